@@ -1,0 +1,193 @@
+// kernels_encode.cu -- board -> network input planes, move -> policy index, and the deterministic test
+// evaluator.
+//
+// Replaces netencoder.get_game_state (netencoder.py:13-91) and the uci_dict gather of
+// AgentDistributed.predict_policy (agentdistributed.py:31-32, 80-82).
+//
+// Plane layout written here: bf16 [row][8][8][128] NHWC, row 0 = rank 8, column 0 = file a; channel
+// 14*s + {0: no black piece, 1..6: black P N B R Q K, 7: no white piece, 8..13: white P..K} for state s
+// (s = 0 current position, s = 1..8 after undoing s plies, all-zero when the move stack is shorter),
+// channel 126 = side to move (1 = white), channel 127 = zero padding so K is a multiple of 64 for the
+// tcgen05 convolution.  HBM-bound: 580 B read, 16,384 B written per position, 16-byte stores, a full
+// 2 KB contiguous span per block-wide store.
+#include "engine.cuh"
+#include "hash_eval.cuh"
+
+namespace crl {
+
+static constexpr int ENC_THREADS = 128;
+
+struct EncShared {
+  u64 bb[9][8];
+  int avail;   // number of states present (1 + min(8, ply))
+  int turn;
+};
+
+// all threads of the block write the 64 x 128 plane tile of one position
+__device__ __forceinline__ void write_planes(const EncShared& s, __nv_bfloat16* __restrict__ out) {
+  uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int id = j * ENC_THREADS + threadIdx.x;   // 16-byte chunk id: 64 squares x 16 chunks
+    const int cell = id >> 4, chunk = id & 15;
+    const int h = cell >> 3, w = cell & 7;
+    const int sq = (7 - h) * 8 + w;
+    unsigned bits = 0;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int c = chunk * 8 + t;
+      unsigned v = 0;
+      if (c < 126) {
+        const int st = c / 14, k = c - st * 14;
+        if (st < s.avail) {
+          const int white = k >= 7;
+          const int kk = white ? k - 7 : k;
+          const u64 side = s.bb[st][white ? OCC_W : OCC_B];
+          if (kk == 0) v = ((side >> sq) & 1) ? 0u : 1u;
+          else v = (unsigned)(((s.bb[st][kk - 1] & side) >> sq) & 1);
+        }
+      } else if (c == 126) {
+        v = (unsigned)s.turn;
+      }
+      bits |= v << t;
+    }
+    uint4 q;
+    q.x = ((bits & 1) ? 0x3F80u : 0u) | ((bits & 2) ? 0x3F800000u : 0u);
+    q.y = ((bits & 4) ? 0x3F80u : 0u) | ((bits & 8) ? 0x3F800000u : 0u);
+    q.z = ((bits & 16) ? 0x3F80u : 0u) | ((bits & 32) ? 0x3F800000u : 0u);
+    q.w = ((bits & 64) ? 0x3F80u : 0u) | ((bits & 128) ? 0x3F800000u : 0u);
+    dst[id] = q;
+  }
+}
+
+// stateless: boards + explicit history arrays
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_boards(const u64* __restrict__ boards,
+                                                               const u64* __restrict__ hist,
+                                                               const u8* __restrict__ hist_len, int n,
+                                                               __nv_bfloat16* __restrict__ planes) {
+  __shared__ EncShared s;
+  const int i = blockIdx.x;
+  if (threadIdx.x < 72) {
+    const int st = threadIdx.x >> 3, k = threadIdx.x & 7;
+    const int hl = (hist && hist_len) ? min((int)hist_len[i], 8) : 0;
+    u64 v = 0;
+    if (st == 0) v = boards[(long long)k * n + i];
+    else if (st - 1 < hl) v = hist[((long long)(st - 1) * 8 + k) * n + i];
+    s.bb[st][k] = v;
+    if (threadIdx.x == 0) {
+      s.avail = 1 + hl;
+      s.turn = (int)(boards[8LL * n + i] & 1);
+    }
+  }
+  __syncthreads();
+  write_planes(s, planes + (long long)i * 64 * 128);
+}
+
+// tree / game batches: row r -> game eval_list[r]; position = (s_node[g], which) or the root when which==0
+__global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
+                                                             __nv_bfloat16* __restrict__ planes) {
+  __shared__ EncShared s;
+  const int r = blockIdx.x;
+  if (r >= *P.eval_n) return;
+  const int g = P.eval_list[r];
+  if (threadIdx.x == 0) {
+    const int node = which == 0 ? 0 : P.s_node[g];
+    const int w = which == 0 ? 2 : which;
+    const NodeRec& nr = P.nodes[(long long)g * P.NN + node];
+    const u64 meta = (w == 2 ? nr.p2 : nr.p1)[8];
+    Cursor c{node, w, meta_ply(meta)};
+    cursor_bitboards(P, g, c, s.bb[0]);
+    int cnt = 1;
+    while (cnt < 9 && cursor_prev(P, g, c)) {
+      cursor_bitboards(P, g, c, s.bb[cnt]);
+      ++cnt;
+    }
+    s.avail = cnt;
+    s.turn = (int)(meta & 1);
+  }
+  __syncthreads();
+  write_planes(s, planes + (long long)r * 64 * 128);
+}
+
+__global__ void k_policy_index(const u16* __restrict__ moves, const int* __restrict__ counts, int n,
+                               const int16_t* __restrict__ label_of, int16_t* __restrict__ idx) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * MAX_MOVES) return;
+  const int i = (int)(t / MAX_MOVES), k = (int)(t % MAX_MOVES);
+  int16_t v = -1;
+  if (k < counts[i]) {
+    u16 m = moves[t];
+    if (m != MOVE_NONE && mv_promo(m) < 5) v = label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)];
+  }
+  idx[t] = v;
+}
+
+// ---- deterministic test evaluator ---------------------------------------------------------------------
+__device__ __forceinline__ void hash_eval_row(const Board& b, u64 seed, int bits, float* __restrict__ policy_row,
+                                              float* __restrict__ value) {
+  const u64 h = eval_hash(b, seed);
+  for (int l = threadIdx.x; l < CRL_N_LABELS; l += blockDim.x) policy_row[l] = hash_policy(h, l, bits);
+  if (threadIdx.x == 0) *value = hash_value(h);
+}
+
+__global__ void __launch_bounds__(256) k_hash_eval_boards(const u64* __restrict__ boards, int n, u64 seed,
+                                                          int bits, float* __restrict__ policy,
+                                                          float* __restrict__ value) {
+  const int i = blockIdx.x;
+  Board b = load_soa(boards, n, i);
+  hash_eval_row(b, seed, bits, policy + (long long)i * CRL_N_LABELS, value + i);
+}
+
+__global__ void __launch_bounds__(256) k_hash_eval_rows(Pools P, int which, u64 seed, int bits,
+                                                        float* __restrict__ policy, float* __restrict__ value) {
+  const int r = blockIdx.x;
+  if (r >= *P.eval_n) return;
+  const int g = P.eval_list[r];
+  const int node = which == 0 ? 0 : P.s_node[g];
+  const NodeRec& nr = P.nodes[(long long)g * P.NN + node];
+  Board b = load_rec((which == 1) ? nr.p1 : nr.p2);
+  hash_eval_row(b, seed, bits, policy + (long long)r * CRL_N_LABELS, value + r);
+}
+
+int launch_encode_boards(crl_engine_impl* e, const u64* boards, const u64* hist, const u8* hist_len, int n,
+                         __nv_bfloat16* planes) {
+  if (n <= 0) return CRL_OK;
+  LaunchScope ls(e, KC_ENCODE);
+  k_encode_boards<<<n, ENC_THREADS, 0, e->stream>>>(boards, hist, hist_len, n, planes);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+int launch_policy_index(crl_engine_impl* e, const u16* moves, const int* counts, int n, int16_t* idx) {
+  if (n <= 0) return CRL_OK;
+  LaunchScope ls(e, KC_ENCODE);
+  k_policy_index<<<div_up((long long)n * MAX_MOVES, 256), 256, 0, e->stream>>>(moves, counts, n, e->d_label_of, idx);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+int launch_hash_eval_boards(crl_engine_impl* e, const u64* boards, int n, u64 seed, int bits, float* policy,
+                            float* value) {
+  if (n <= 0) return CRL_OK;
+  LaunchScope ls(e, KC_HASHEVAL);
+  k_hash_eval_boards<<<n, 256, 0, e->stream>>>(boards, n, seed, bits, policy, value);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+// Encodes the positions named by P.eval_list (which: 0 root, 1 state after our move, 2 node state) and runs
+// the configured evaluator on them; results land in e->d_policy / e->d_value, row r <-> game eval_list[r].
+int launch_eval_batch(crl_engine_impl* e, int which) {
+  if (e->eval_kind == CRL_EVAL_HASH) {
+    LaunchScope ls(e, KC_HASHEVAL);
+    k_hash_eval_rows<<<e->G, 256, 0, e->stream>>>(e->P, which, e->eval_seed, e->eval_bits, e->d_policy, e->d_value);
+    CRL_CUDA(cudaGetLastError());
+    return CRL_OK;
+  }
+  {
+    LaunchScope ls(e, KC_ENCODE);
+    k_encode_rows<<<e->G, ENC_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
+    CRL_CUDA(cudaGetLastError());
+  }
+  return net_forward(e, e->d_planes, e->G, e->P.eval_n, e->d_policy, e->d_value);
+}
+
+}  // namespace crl

@@ -1,0 +1,328 @@
+// kernels_tree.cu -- the lockstep PUCT search kernels and the game-record kernels.
+//
+// One simulation of every running game (SelfPlayTree.explore_tree, mctree.py:200-214) is the fixed kernel
+// sequence  select+expand -> [evaluate P1] -> reply -> [evaluate P2] -> finalize+backup ; games that need
+// no network evaluation in a phase (terminal leaves) simply do not enter that phase's compacted batch.
+//   * k_select_expand : one WARP per game.  The warp walks down from the root; at every fully expanded node
+//     the 32 lanes scan the node's contiguous edge statistics (visits i32, value f64, prior f32, result i8)
+//     with coalesced loads, score them in float64 exactly as Node.get_value does, and reduce to the FIRST
+//     maximum with shuffles (np.argmax semantics).  Lane 0 then pops the last unexpanded action and creates
+//     the child.
+//   * k_reply / k_finalize : one thread per batch row / per game (movegen + make-move are per-thread code).
+// With one in-flight simulation per game (the reference's deterministic threads=1 schedule) no atomics are
+// needed on the statistics; the only atomics are the batch-compaction counters.
+#include "engine.cuh"
+
+#include <math_constants.h>
+
+namespace crl {
+
+static constexpr int TREE_BLOCK = 128;
+
+__device__ __forceinline__ bool game_running(const Pools& P, int g) {
+  return P.g_active[g] && P.g_result[g] == RESULT_NONE;
+}
+
+struct WarpScan {
+  const Pools& P;
+  int g, lane;
+  __device__ __forceinline__ int operator()(const NodeRec& n) const {
+    const long long base = (long long)g * P.EA + n.edge0;
+    const int cnt = n.n_exp;
+    double best_s = -CUDART_INF;
+    int best_k = 0x7fffffff;
+    for (int k = lane; k < cnt; k += 32) {
+      double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k]);
+      if (s > best_s) {
+        best_s = s;
+        best_k = k;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      double os = __shfl_xor_sync(0xffffffffu, best_s, off);
+      int ok = __shfl_xor_sync(0xffffffffu, best_k, off);
+      if (os > best_s || (os == best_s && ok < best_k)) {
+        best_s = os;
+        best_k = ok;
+      }
+    }
+    return best_k;
+  }
+};
+
+__global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= P.G) return;
+  if (!game_running(P, g)) {
+    if (lane == 0) P.s_kind[g] = KIND_IDLE;
+    return;
+  }
+  int node, term;
+  select_descend(P, g, WarpScan{P, g, lane}, &node, &term);
+  if (lane != 0) return;
+  if (term) {
+    P.s_node[g] = node;
+    P.s_kind[g] = KIND_TERMINAL;
+    return;
+  }
+  int child;
+  int kind = expand_child(P, g, node, &child);
+  P.s_node[g] = child;
+  P.s_kind[g] = kind;
+  if (kind == KIND_NEED_REPLY) {
+    int row = atomicAdd(P.eval_n, 1);
+    P.eval_list[row] = g;
+    P.s_row[g] = row;
+  }
+}
+
+// rows of batch A (positions after our move) -> opponent reply, node state, batch B
+__global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __restrict__ policy,
+                                                      const int16_t* __restrict__ label_of, int* list_b,
+                                                      int* n_b) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_a = *P.eval_n;
+  if (r == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
+  if (r >= n_a) return;
+  const int g = P.eval_list[r];
+  const int child = P.s_node[g];
+  int kind = reply_child(P, g, child, policy + (long long)r * CRL_N_LABELS, label_of);
+  P.s_kind[g] = kind;
+  if (kind == KIND_EVAL_LEAF) {
+    int row = atomicAdd(n_b, 1);
+    list_b[row] = g;
+    P.s_row[g] = row;
+  }
+}
+
+// SelfPlayTree.simulate + backprop (mctree.py:259-296) for every running game
+__global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* __restrict__ policy,
+                                                         const float* __restrict__ value,
+                                                         const int16_t* __restrict__ label_of) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)*P.eval_n);
+  bool live = g < P.G && game_running(P, g) && P.s_kind[g] != KIND_IDLE;
+  unsigned m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long*)&P.counters[0], (unsigned long long)__popc(m));
+  if (!live) return;
+  const int node = P.s_node[g];
+  const int kind = P.s_kind[g];
+  double v;
+  if (kind == KIND_EVAL_LEAF) {
+    const int row = P.s_row[g];
+    store_priors(P, g, node, policy + (long long)row * CRL_N_LABELS, label_of);
+    v = (double)value[row];                                   // float(v) of a float32 (predict_worker.py:111)
+  } else {
+    v = (double)P.nodes[(long long)g * P.NN + node].result;   // terminal: Game.get_result (mctree.py:268)
+  }
+  backup(P, g, node, v);
+}
+
+// Tree(root): build node 0 of every running game and queue it for evaluation
+__global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __restrict__ mask) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.G) return;
+  P.s_kind[g] = KIND_IDLE;
+  if (!game_running(P, g) || (mask && !mask[g])) return;
+  root_init(P, g);
+  P.s_node[g] = 0;
+  int row = atomicAdd(P.eval_n, 1);
+  P.eval_list[row] = g;
+  P.s_row[g] = row;
+}
+
+__global__ void __launch_bounds__(TREE_BLOCK) k_root_priors(Pools P, const float* __restrict__ policy,
+                                                            const int16_t* __restrict__ label_of) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = *P.eval_n;
+  if (r == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n);
+  if (r >= n) return;
+  const int g = P.eval_list[r];
+  store_priors(P, g, 0, policy + (long long)r * CRL_N_LABELS, label_of);
+}
+
+// AgentDistributed.best_move(real_game=True): argmax of the legal-masked policy of the current position
+__global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, const float* __restrict__ policy,
+                                                            const int16_t* __restrict__ label_of,
+                                                            u16* __restrict__ picks) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= *P.eval_n) return;
+  const int g = P.eval_list[r];
+  const NodeRec& root = P.nodes[(long long)g * P.NN];
+  const u16* moves = P.e_move + (long long)g * P.EA + root.edge0;
+  u16 mv = MOVE_NONE;
+  if (root.n_legal > 0) mv = moves[argmax_legal(policy + (long long)r * CRL_N_LABELS, label_of, moves, root.n_legal)];
+  picks[g] = mv;
+  game_move(P, g, mv);
+}
+
+// ---- game records -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first, int n,
+                                                             const u64* __restrict__ start_aos,
+                                                             const u16* __restrict__ moves,
+                                                             const int* __restrict__ n_moves, int stride,
+                                                             u8* __restrict__ accepted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int g = first + i;
+  Board b = load_rec(start_aos + 9LL * i);
+  // a fresh record starts with an empty move stack (Board(fen) / Game())
+  b.meta = meta_pack(meta_turn(b.meta), meta_castle(b.meta), meta_ep(b.meta), meta_halfmove(b.meta),
+                     meta_fullmove(b.meta), 0, 0);
+  store_soa(P.g_cur, P.G, g, b);
+  P.g_nmoves[g] = 0;
+  P.g_active[g] = 1;
+  P.g_nnodes[g] = 0;
+  game_refresh(P, g, nullptr, nullptr);
+  const int m = n_moves ? n_moves[i] : 0;
+  for (int k = 0; k < m; ++k) {
+    int ok = game_move(P, g, moves[(long long)i * stride + k]);
+    if (accepted) accepted[(long long)i * stride + k] = (u8)ok;
+  }
+}
+
+// what game.Game exposes about the current position: legal moves (python-chess order) and get_result
+__global__ void __launch_bounds__(TREE_BLOCK) k_game_info(Pools P, int first, int n, u16* __restrict__ legal,
+                                                          int* __restrict__ n_legal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Board b = load_soa(P.g_cur, P.G, first + i);
+  StoreSink sink{legal + (long long)i * MAX_MOVES, 0};
+  generate_legal(b, sink);
+  n_legal[i] = sink.n;
+}
+
+// one optional move per game (MOVE_NONE = none), through Game.move's legality check
+__global__ void __launch_bounds__(TREE_BLOCK) k_game_moves(Pools P, const u16* __restrict__ mv,
+                                                           u8* __restrict__ accepted) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.G) return;
+  int ok = 0;
+  if (P.g_active[g] && mv[g] != MOVE_NONE) ok = game_move(P, g, mv[g]);
+  if (accepted) accepted[g] = (u8)ok;
+}
+
+// search_move's return value (mctree.py:178-198) for the chosen root child of every game
+__global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __restrict__ pick,
+                                                       u16* __restrict__ out_moves, int apply) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.G) return;
+  u16 m0 = MOVE_NONE, m1 = MOVE_NONE;
+  const int k = pick[g];
+  const NodeRec& root = P.nodes[(long long)g * P.NN];
+  if (P.g_active[g] && k >= 0 && k < root.n_exp) {
+    const NodeRec& c = P.nodes[(long long)g * P.NN + P.e_child[(long long)g * P.EA + root.edge0 + k]];
+    if (c.reply != MOVE_NONE) {
+      m0 = c.move;             // move_stack[-2] = our move, [-1] = the opponent's reply
+      m1 = c.reply;
+    } else if (P.g_nmoves[g] >= 1) {
+      m0 = P.g_moves[(long long)g * MAX_GAME_PLIES + P.g_nmoves[g] - 1];   // previous ply (reference quirk)
+      m1 = c.move;
+    }                          // else: IndexError in the reference -> both stay the null move
+  }
+  out_moves[2 * g] = m0;
+  out_moves[2 * g + 1] = m1;
+  if (apply && P.g_active[g] && k >= 0) {
+    game_move(P, g, m0);       // selfplay.py:77-78: Game.move silently rejects an illegal first move
+    game_move(P, g, m1);
+  }
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------
+int launch_games_replay(crl_engine_impl* e, int first, int n, const u64* start_aos, const u16* moves,
+                        const int* n_moves, int stride, u8* accepted) {
+  LaunchScope ls(e, KC_GAME);
+  k_games_replay<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, start_aos, moves, n_moves, stride,
+                                                                      accepted);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+int launch_game_info(crl_engine_impl* e, int first, int n, u16* legal, int* n_legal) {
+  LaunchScope ls(e, KC_GAME);
+  k_game_info<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, legal, n_legal);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+int launch_game_moves(crl_engine_impl* e, const u16* mv, u8* accepted) {
+  LaunchScope ls(e, KC_GAME);
+  k_game_moves<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mv, accepted);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+
+static int use_list(crl_engine_impl* e, int which) {
+  e->P.eval_list = e->d_list[which];
+  e->P.eval_n = e->d_n + which;
+  return CRL_OK;
+}
+
+// Tree(root) for every running game (or the masked subset): node 0, its legal moves, its priors
+int tree_begin_move(crl_engine_impl* e, const u8* mask_dev) {
+  CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
+  use_list(e, 0);
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_root_init<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mask_dev);
+    CRL_CUDA(cudaGetLastError());
+  }
+  int rc = launch_eval_batch(e, 0);
+  if (rc != CRL_OK) return rc;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_root_priors<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of);
+    CRL_CUDA(cudaGetLastError());
+  }
+  return CRL_OK;
+}
+
+int tree_simulate(crl_engine_impl* e, int n_sims) {
+  for (int s = 0; s < n_sims; ++s) {
+    CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
+    use_list(e, 0);
+    {
+      LaunchScope ls(e, KC_TREE);
+      k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
+      CRL_CUDA(cudaGetLastError());
+    }
+    int rc = launch_eval_batch(e, 1);
+    if (rc != CRL_OK) return rc;
+    {
+      LaunchScope ls(e, KC_TREE);
+      k_reply<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                       e->d_list[1], e->d_n + 1);
+      CRL_CUDA(cudaGetLastError());
+    }
+    use_list(e, 1);
+    rc = launch_eval_batch(e, 2);
+    if (rc != CRL_OK) return rc;
+    {
+      LaunchScope ls(e, KC_TREE);
+      k_finalize<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
+                                                                          e->d_label_of);
+      CRL_CUDA(cudaGetLastError());
+    }
+  }
+  return CRL_OK;
+}
+
+int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev) {
+  CRL_CUDA(cudaMemsetAsync(picks_dev, 0xFF, sizeof(u16) * e->G, e->stream));
+  int rc = tree_begin_move(e, mask_dev);   // root_init + evaluation of the current positions
+  if (rc != CRL_OK) return rc;
+  LaunchScope ls(e, KC_TREE);
+  k_policy_move<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, picks_dev);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+int tree_commit(crl_engine_impl* e, const int* pick_dev, u16* out_moves_dev, int apply) {
+  LaunchScope ls(e, KC_GAME);
+  k_commit<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, pick_dev, out_moves_dev, apply);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+}  // namespace crl

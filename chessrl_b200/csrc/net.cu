@@ -1,0 +1,740 @@
+// net.cu -- forward pass of the policy/value ResNet (model.ChessModel, model.py:31-63, 111-122) for sm_100a.
+//
+// The 21 3x3 convolutions (1 stem + 10 residual blocks x 2) are >99.9% of the FLOPs (1.548 GFLOP/position)
+// and run as ONE kernel each: an implicit GEMM on the 5th-generation tensor cores.
+//
+//   GEMM view      D[M = 64*B board squares][N = 256 filters] = A[M][K = 9*Cin] * W[K][N]
+//   A operand      never materialised.  Activations stay NHWC bf16 [B][8][8][Cin]; for filter tap (dy,dx) and a
+//                  64-channel slice, one TMA box {64ch, 8, 8, 2 boards} fetched at coordinates
+//                  {c0, dx, dy, 2*tile} IS the im2col tile: rows that fall off the board are zero-filled by
+//                  the TMA unit's out-of-bounds handling ('same' padding), and the box lands in shared memory
+//                  as 128 rows x 128 B with the 128-byte swizzle tcgen05 expects for a K-major operand.
+//   B operand      weights re-laid out once as [256][9*Cin] bf16 (K-major), one TMA box {64, 256} per k-block.
+//   MMA            tcgen05.mma.cta_group::1.kind::f16, M=128 N=256 K=16, issued by one thread, fp32 accumulators
+//                  in tensor memory (2 x 256 columns, double buffered so the epilogue of tile i overlaps the
+//                  MMAs of tile i+1).
+//   pipeline       4-stage shared-memory ring (48 KB per stage) fed by a TMA producer thread; mbarriers
+//                  full/empty per stage, tmem_full/tmem_empty per accumulator.
+//   epilogue       4 warps: tcgen05.ld (32 lanes x 32 columns per instruction), folded BatchNorm scale/shift
+//                  (+bias), optional residual add and ReLU in fp32, bf16 pack, 16-byte stores to NHWC.
+//   scheduling     persistent: one CTA per SM, tiles of 2 boards strided over the grid; the row count is
+//                  read from device memory so search batches compact without a host round trip.
+//
+// The heads (1x1 convs, Dense 128->1968 softmax, Dense 64->256->1 tanh: 0.04% of the FLOPs) are one
+// CUDA-core kernel over 8 positions per block.
+#include "engine.cuh"
+
+#include <cuda.h>
+#include <math.h>
+#include <string.h>
+
+namespace crl {
+
+// ======================================================================================================
+// PTX wrappers
+// ======================================================================================================
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded spin: a protocol bug traps (reported as a CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory operand descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (unused here) | [32,46) SBO>>4 = 8 rows * 128 B | [46,48) version=1 |
+// [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ======================================================================================================
+// the 3x3 convolution kernel
+// ======================================================================================================
+static constexpr int CONV_THREADS = 256;
+static constexpr int CONV_STAGES = 4;
+static constexpr int TILE_M = 128;                       // 2 boards x 64 squares
+static constexpr int TILE_N = 256;                       // all filters
+static constexpr int BLOCK_K = 64;                       // one 128-byte swizzle atom of bf16
+static constexpr int A_STAGE_BYTES = TILE_M * BLOCK_K * 2;   // 16 KB
+static constexpr int B_STAGE_BYTES = TILE_N * BLOCK_K * 2;   // 32 KB
+static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+static constexpr int CONV_SMEM_BYTES = 1024 /*align slack*/ + CONV_STAGES * STAGE_BYTES + 2 * TILE_N * 4 + 256;
+// instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, N=256, M=128
+static constexpr uint32_t CONV_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TILE_N >> 3) << 17) | ((TILE_M >> 4) << 24);
+
+struct ConvParams {
+  const int* n_rows_dev;        // board count on the device (or null)
+  int n_rows_host;              // board count / upper bound
+  int k_chunks;                 // Cin / 64
+  const float* scale;           // [256] folded BatchNorm scale (1 when the layer has no BN)
+  const float* shift;           // [256] folded bias / BatchNorm shift
+  const __nv_bfloat16* residual;  // [rows][64][256] or null
+  __nv_bfloat16* out;           // [rows][64][256]
+  int relu;
+};
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+k_conv3x3(const __grid_constant__ CUtensorMap map_act, const __grid_constant__ CUtensorMap map_w, ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // 128B swizzle: 1024-aligned
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + CONV_STAGES * A_STAGE_BYTES;
+  float* s_scale = (float*)(smem + CONV_STAGES * STAGE_BYTES);
+  float* s_shift = s_scale + TILE_N;
+  uint64_t* bars = (uint64_t*)(s_shift + TILE_N);
+  uint64_t* full_bar = bars;                    // [CONV_STAGES]
+  uint64_t* empty_bar = bars + CONV_STAGES;     // [CONV_STAGES]
+  uint64_t* tmem_full = bars + 2 * CONV_STAGES; // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n_rows = p.n_rows_host;
+  if (p.n_rows_dev) n_rows = min(n_rows, *p.n_rows_dev);
+  const int n_tiles = (n_rows + 1) >> 1;
+  const int n_kblocks = 9 * p.k_chunks;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_act);
+    prefetch_tmap(&map_w);
+  }
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < CONV_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < TILE_N; i += CONV_THREADS) {
+    s_scale[i] = p.scale[i];
+    s_shift[i] = p.shift[i];
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        const int tap = kb / p.k_chunks, kc = kb - tap * p.k_chunks;
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+        tma_load_4d(smem_a + stage * A_STAGE_BYTES, &map_act, &full_bar[stage], kc * BLOCK_K, dx, dy, tile * 2);
+        tma_load_2d(smem_b + stage * B_STAGE_BYTES, &map_w, &full_bar[stage], kb * BLOCK_K, 0);
+        if (++stage == CONV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (threadIdx.x == 32) {
+    // ================= MMA issuer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * TILE_N;
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
+        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advancing K by 16 bf16 = 32 bytes inside the swizzle atom = +2 in the (addr >> 4) field
+          umma_bf16(tmem_d, da + 2 * k, db + 2 * k, CONV_IDESC, (kb | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);                   // frees the smem stage when these MMAs retire
+        if (kb == n_kblocks - 1) umma_commit(&tmem_full[acc]);   // accumulator complete
+        if (++stage == CONV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue: TMEM -> registers -> BN/residual/ReLU -> bf16 -> global =================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may read
+    const int row_in_tile = q * 32 + lane;      // GEMM row = accumulator lane
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const long long grow = (long long)tile * TILE_M + row_in_tile;     // global row = board*64 + square
+      const bool valid = grow < (long long)n_rows * 64;
+      __nv_bfloat16* orow = p.out + grow * TILE_N;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * TILE_N : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TILE_N + c0, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4 res[4];
+          if (rrow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + c0 + 8 * j);
+          }
+          uint4 outv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t packed[4];
+            const uint32_t* rj = reinterpret_cast<const uint32_t*>(&res[j]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int c = c0 + 8 * j + 2 * h;
+              float a0 = __uint_as_float(v[8 * j + 2 * h]) * s_scale[c] + s_shift[c];
+              float a1 = __uint_as_float(v[8 * j + 2 * h + 1]) * s_scale[c + 1] + s_shift[c + 1];
+              if (rrow) {
+                a0 += __uint_as_float(rj[h] << 16);
+                a1 += __uint_as_float(rj[h] & 0xFFFF0000u);
+              }
+              if (p.relu) {
+                a0 = fmaxf(a0, 0.f);
+                a1 = fmaxf(a1, 0.f);
+              }
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(a0, a1);
+              packed[h] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            outv[j] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = outv[j];
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ======================================================================================================
+// heads: 1x1 convs + BN + ReLU, Dense 128->1968 softmax, Dense 64->256 ReLU -> Dense 256->1 tanh
+// ======================================================================================================
+static constexpr int HEAD_POS = 8;        // positions per block
+static constexpr int HEAD_THREADS = 256;
+
+struct HeadParams {
+  const int* n_rows_dev;
+  int n_rows_host;
+  const __nv_bfloat16* x;      // [rows][64][256] trunk output
+  const float* w1x1;           // [3][256]: policy ch0, policy ch1, value ch
+  const float* s1x1;           // [3] folded scale, [3] folded shift
+  const float* wp;             // [128][1968]
+  const float* bp;             // [1968]
+  const float* wv1;            // [64][256]
+  const float* bv1;            // [256]
+  const float* wv2;            // [256]
+  const float* bv2;            // [1]
+  float* policy;               // [rows][1968]
+  float* value;                // [rows]
+};
+
+__global__ void __launch_bounds__(HEAD_THREADS) k_heads(HeadParams p) {
+  extern __shared__ float hs[];
+  float* s_w = hs;                              // [3][256]
+  float* s_pf = s_w + 3 * 256;                  // [HEAD_POS][128] policy features (h,w,c) flatten
+  float* s_vf = s_pf + HEAD_POS * 128;          // [HEAD_POS][64]
+  float* s_hid = s_vf + HEAD_POS * 64;          // [HEAD_POS][256]
+  float* s_logit = s_hid + HEAD_POS * 256;      // [HEAD_POS][1968]
+  int n_rows = p.n_rows_host;
+  if (p.n_rows_dev) n_rows = min(n_rows, *p.n_rows_dev);
+  const int pos0 = blockIdx.x * HEAD_POS;
+  if (pos0 >= n_rows) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 3 * 256; i += HEAD_THREADS) s_w[i] = p.w1x1[i];
+  __syncthreads();
+
+  // (1) 1x1 convolutions: warp w owns position pos0+w; lanes split the 256 channels 8 apiece
+  {
+    const int pos = pos0 + warp;
+    const bool ok = pos < n_rows;
+    for (int sq = 0; sq < 64; ++sq) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (ok) {
+        uint4 raw = *reinterpret_cast<const uint4*>(p.x + ((long long)pos * 64 + sq) * 256 + lane * 8);
+        const uint32_t* r = reinterpret_cast<const uint32_t*>(&raw);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          float x0 = __uint_as_float(r[h] << 16), x1 = __uint_as_float(r[h] & 0xFFFF0000u);
+          int c = lane * 8 + 2 * h;
+          a0 += x0 * s_w[c] + x1 * s_w[c + 1];
+          a1 += x0 * s_w[256 + c] + x1 * s_w[256 + c + 1];
+          a2 += x0 * s_w[512 + c] + x1 * s_w[512 + c + 1];
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, off);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+      }
+      if (lane == 0) {
+        s_pf[warp * 128 + sq * 2 + 0] = fmaxf(a0 * p.s1x1[0] + p.s1x1[3], 0.f);
+        s_pf[warp * 128 + sq * 2 + 1] = fmaxf(a1 * p.s1x1[1] + p.s1x1[4], 0.f);
+        s_vf[warp * 64 + sq] = fmaxf(a2 * p.s1x1[2] + p.s1x1[5], 0.f);
+      }
+    }
+  }
+  __syncthreads();
+
+  // (2) policy logits: thread owns output columns j, j+256, ...; weights stream from L2 once per 8 positions
+  for (int j = threadIdx.x; j < CRL_N_LABELS; j += HEAD_THREADS) {
+    float acc[HEAD_POS];
+#pragma unroll
+    for (int q = 0; q < HEAD_POS; ++q) acc[q] = 0.f;
+    for (int i = 0; i < 128; ++i) {
+      const float w = p.wp[(long long)i * CRL_N_LABELS + j];
+#pragma unroll
+      for (int q = 0; q < HEAD_POS; ++q) acc[q] = fmaf(s_pf[q * 128 + i], w, acc[q]);
+    }
+    const float b = p.bp[j];
+#pragma unroll
+    for (int q = 0; q < HEAD_POS; ++q) s_logit[q * CRL_N_LABELS + j] = acc[q] + b;
+  }
+  // value hidden layer: thread j owns hidden unit j
+  {
+    const int j = threadIdx.x;
+    float acc[HEAD_POS];
+#pragma unroll
+    for (int q = 0; q < HEAD_POS; ++q) acc[q] = 0.f;
+    for (int i = 0; i < 64; ++i) {
+      const float w = p.wv1[i * 256 + j];
+#pragma unroll
+      for (int q = 0; q < HEAD_POS; ++q) acc[q] = fmaf(s_vf[q * 64 + i], w, acc[q]);
+    }
+    const float b = p.bv1[j];
+#pragma unroll
+    for (int q = 0; q < HEAD_POS; ++q) s_hid[q * 256 + j] = fmaxf(acc[q] + b, 0.f);
+  }
+  __syncthreads();
+
+  // (3) softmax and value output: warp w finishes position pos0+w
+  {
+    const int pos = pos0 + warp;
+    if (pos < n_rows) {
+      const float* lg = s_logit + warp * CRL_N_LABELS;
+      float m = -INFINITY;
+      for (int j = lane; j < CRL_N_LABELS; j += 32) m = fmaxf(m, lg[j]);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+      float s = 0.f;
+      for (int j = lane; j < CRL_N_LABELS; j += 32) s += expf(lg[j] - m);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      const float inv = 1.0f / s;
+      float* out = p.policy + (long long)pos * CRL_N_LABELS;
+      for (int j = lane; j < CRL_N_LABELS; j += 32) out[j] = expf(lg[j] - m) * inv;
+      float v = 0.f;
+      for (int j = lane; j < 256; j += 32) v = fmaf(s_hid[warp * 256 + j], p.wv2[j], v);
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0) p.value[pos] = tanhf(v + p.bv2[0]);
+    }
+  }
+}
+static constexpr int HEAD_SMEM_BYTES = (3 * 256 + HEAD_POS * (128 + 64 + 256 + CRL_N_LABELS)) * 4;
+
+// ======================================================================================================
+// host side: weight pack, tensor maps, forward
+// ======================================================================================================
+static constexpr int N_CONVS = 21;
+static constexpr float BN_EPS = 1e-3f;   // Keras BatchNormalization default
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct NetWeights {
+  int cap_rows = 0;                         // activation capacity in boards (even)
+  bool loaded = false;
+  __nv_bfloat16* w[N_CONVS] = {nullptr};    // [256][9*Cin] K-major
+  float* scale[N_CONVS] = {nullptr};
+  float* shift[N_CONVS] = {nullptr};
+  int cin[N_CONVS] = {0};
+  CUtensorMap map_w[N_CONVS];
+  __nv_bfloat16* act[2] = {nullptr, nullptr};   // [cap][64][256]
+  CUtensorMap map_act[2];
+  CUtensorMap map_planes;
+  const void* planes_ptr = nullptr;
+  int planes_rows = 0;
+  float *w1x1 = nullptr, *s1x1 = nullptr, *wp = nullptr, *bp = nullptr, *wv1 = nullptr, *bv1 = nullptr,
+        *wv2 = nullptr, *bv2 = nullptr;
+  PFN_encodeTiled encode = nullptr;
+  int n_sms = 148;
+};
+
+static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int cin, int rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)cin, 8, 8, (cuuint64_t)rows};
+  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 16, (cuuint64_t)cin * 128};
+  cuuint32_t box[4] = {BLOCK_K, 8, 8, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = nw->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    return CRL_ECUDA;
+  }
+  return CRL_OK;
+}
+static int make_w_map(NetWeights* nw, CUtensorMap* map, const void* base, int k_total) {
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, TILE_N};
+  cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
+  cuuint32_t box[2] = {BLOCK_K, TILE_N};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = nw->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    return CRL_ECUDA;
+  }
+  return CRL_OK;
+}
+
+template <class T>
+static int dev_alloc(crl_engine_impl* e, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t err = cudaMalloc(&q, count * sizeof(T));
+  if (err != cudaSuccess) {
+    set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
+    return CRL_ENOMEM;
+  }
+  e->allocs.push_back(q);
+  *p = (T*)q;
+  return CRL_OK;
+}
+
+int net_create(crl_engine_impl* e) {
+  NetWeights* nw = new NetWeights();
+  e->net = nw;
+  nw->cap_rows = (e->G + 2) & ~1;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (err != cudaSuccess || fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver: %s", cudaGetErrorString(err));
+    return CRL_ECUDA;
+  }
+  nw->encode = (PFN_encodeTiled)fn;
+  int dev = e->device;
+  cudaDeviceGetAttribute(&nw->n_sms, cudaDevAttrMultiProcessorCount, dev);
+  int rc;
+  for (int i = 0; i < N_CONVS; ++i) {
+    nw->cin[i] = i == 0 ? 128 : 256;
+    if ((rc = dev_alloc(e, &nw->w[i], (size_t)TILE_N * 9 * nw->cin[i]))) return rc;
+    if ((rc = dev_alloc(e, &nw->scale[i], 256))) return rc;
+    if ((rc = dev_alloc(e, &nw->shift[i], 256))) return rc;
+    if ((rc = make_w_map(nw, &nw->map_w[i], nw->w[i], 9 * nw->cin[i]))) return rc;
+  }
+  for (int i = 0; i < 2; ++i) {
+    if ((rc = dev_alloc(e, &nw->act[i], (size_t)nw->cap_rows * 64 * 256))) return rc;
+    CRL_CUDA(cudaMemsetAsync(nw->act[i], 0, (size_t)nw->cap_rows * 64 * 256 * 2, e->stream));
+    if ((rc = make_act_map(nw, &nw->map_act[i], nw->act[i], 256, nw->cap_rows))) return rc;
+  }
+  if ((rc = dev_alloc(e, &nw->w1x1, 3 * 256))) return rc;
+  if ((rc = dev_alloc(e, &nw->s1x1, 6))) return rc;
+  if ((rc = dev_alloc(e, &nw->wp, (size_t)128 * CRL_N_LABELS))) return rc;
+  if ((rc = dev_alloc(e, &nw->bp, CRL_N_LABELS))) return rc;
+  if ((rc = dev_alloc(e, &nw->wv1, 64 * 256))) return rc;
+  if ((rc = dev_alloc(e, &nw->bv1, 256))) return rc;
+  if ((rc = dev_alloc(e, &nw->wv2, 256))) return rc;
+  if ((rc = dev_alloc(e, &nw->bv2, 1))) return rc;
+  CRL_CUDA(cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
+  CRL_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_BYTES));
+  return CRL_OK;
+}
+
+void net_destroy(crl_engine_impl* e) {
+  delete e->net;
+  e->net = nullptr;
+}
+
+static inline uint16_t f2bf(float f) {   // round to nearest even
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7FFFu + ((u >> 16) & 1);
+  return (uint16_t)(u >> 16);
+}
+
+// Weight pack (140 fp32 tensors, Keras layouts), see DESIGN.md:
+//   0,1            stem conv kernel [3][3][127][256], bias [256]
+//   2+12b .. +11   residual block b: conv_a kernel [3][3][256][256], bias, BN gamma, beta, mean, var,
+//                                    conv_b kernel, bias, BN gamma, beta, mean, var
+//   122..129       policy head: conv kernel [1][1][256][2], bias[2], BN gamma,beta,mean,var [2],
+//                               dense kernel [128][1968], bias [1968]
+//   130..139       value head: conv kernel [1][1][256][1], bias[1], BN x4 [1], dense kernel [64][256], bias[256],
+//                              dense kernel [256][1], bias[1]
+int net_load(crl_engine_impl* e, const float* const* w, const int64_t* sizes, int n) {
+  NetWeights* nw = e->net;
+  if (n != CRL_N_WEIGHT_TENSORS) {
+    set_error("crl_net_load_host: expected %d tensors, got %d", CRL_N_WEIGHT_TENSORS, n);
+    return CRL_EINVAL;
+  }
+  auto need = [&](int i, int64_t sz) -> bool {
+    if (sizes[i] != sz) {
+      set_error("crl_net_load_host: tensor %d has %lld elements, expected %lld", i, (long long)sizes[i], (long long)sz);
+      return false;
+    }
+    return true;
+  };
+  std::vector<uint16_t> wt;
+  std::vector<float> sc(256), sh(256);
+  for (int L = 0; L < N_CONVS; ++L) {
+    const int cin_real = L == 0 ? 127 : 256, cin = nw->cin[L];
+    int ik, ib, ibn = -1;
+    if (L == 0) {
+      ik = 0;
+      ib = 1;
+    } else {
+      const int blk = (L - 1) / 2, second = (L - 1) % 2;
+      ik = 2 + 12 * blk + 6 * second;
+      ib = ik + 1;
+      ibn = ik + 2;
+    }
+    if (!need(ik, (int64_t)9 * cin_real * 256) || !need(ib, 256)) return CRL_EINVAL;
+    wt.assign((size_t)256 * 9 * cin, 0);
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < cin_real; ++c)
+        for (int o = 0; o < 256; ++o)
+          wt[(size_t)o * 9 * cin + t * cin + c] = f2bf(w[ik][((size_t)t * cin_real + c) * 256 + o]);
+    for (int o = 0; o < 256; ++o) {
+      float s = 1.f, b = w[ib][o];
+      if (ibn >= 0) {
+        if (!need(ibn, 256) || !need(ibn + 1, 256) || !need(ibn + 2, 256) || !need(ibn + 3, 256)) return CRL_EINVAL;
+        s = w[ibn][o] / sqrtf(w[ibn + 3][o] + BN_EPS);
+        b = (b - w[ibn + 2][o]) * s + w[ibn + 1][o];
+      }
+      sc[o] = s;
+      sh[o] = b;
+    }
+    CRL_CUDA(cudaMemcpyAsync(nw->w[L], wt.data(), wt.size() * 2, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaMemcpyAsync(nw->scale[L], sc.data(), 1024, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaMemcpyAsync(nw->shift[L], sh.data(), 1024, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaStreamSynchronize(e->stream));
+  }
+  // heads
+  const int P0 = 122, V0 = 130;
+  if (!need(P0, 512) || !need(P0 + 1, 2) || !need(P0 + 6, (int64_t)128 * CRL_N_LABELS) || !need(P0 + 7, CRL_N_LABELS) ||
+      !need(V0, 256) || !need(V0 + 1, 1) || !need(V0 + 6, 64 * 256) || !need(V0 + 7, 256) || !need(V0 + 8, 256) ||
+      !need(V0 + 9, 1))
+    return CRL_EINVAL;
+  std::vector<float> w1(3 * 256), s1(6);
+  for (int c = 0; c < 256; ++c) {
+    w1[c] = w[P0][c * 2 + 0];
+    w1[256 + c] = w[P0][c * 2 + 1];
+    w1[512 + c] = w[V0][c];
+  }
+  for (int o = 0; o < 2; ++o) {
+    float s = w[P0 + 2][o] / sqrtf(w[P0 + 5][o] + BN_EPS);
+    s1[o] = s;
+    s1[3 + o] = (w[P0 + 1][o] - w[P0 + 4][o]) * s + w[P0 + 3][o];
+  }
+  {
+    float s = w[V0 + 2][0] / sqrtf(w[V0 + 5][0] + BN_EPS);
+    s1[2] = s;
+    s1[5] = (w[V0 + 1][0] - w[V0 + 4][0]) * s + w[V0 + 3][0];
+  }
+  CRL_CUDA(cudaMemcpyAsync(nw->w1x1, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->s1x1, s1.data(), s1.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->wp, w[P0 + 6], (size_t)128 * CRL_N_LABELS * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->bp, w[P0 + 7], CRL_N_LABELS * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->wv1, w[V0 + 6], 64 * 256 * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->bv1, w[V0 + 7], 256 * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->wv2, w[V0 + 8], 256 * 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(nw->bv2, w[V0 + 9], 4, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));
+  nw->loaded = true;
+  return CRL_OK;
+}
+
+static int launch_conv(crl_engine_impl* e, const CUtensorMap& map_in, int L, const int* n_dev, int n_host,
+                       const __nv_bfloat16* residual, __nv_bfloat16* out, int relu) {
+  NetWeights* nw = e->net;
+  ConvParams p;
+  p.n_rows_dev = n_dev;
+  p.n_rows_host = n_host;
+  p.k_chunks = nw->cin[L] / BLOCK_K;
+  p.scale = nw->scale[L];
+  p.shift = nw->shift[L];
+  p.residual = residual;
+  p.out = out;
+  p.relu = relu;
+  int tiles = (n_host + 1) / 2;
+  int grid = tiles < nw->n_sms ? tiles : nw->n_sms;
+  if (grid < 1) grid = 1;
+  LaunchScope ls(e, KC_CONV);
+  k_conv3x3<<<grid, CONV_THREADS, CONV_SMEM_BYTES, e->stream>>>(map_in, nw->map_w[L], p);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, const int* n_dev, float* policy,
+                float* value) {
+  NetWeights* nw = e->net;
+  if (!nw || !nw->loaded) {
+    set_error("network weights are not loaded (crl_net_load_host)");
+    return CRL_ESTATE;
+  }
+  if (n_host <= 0) return CRL_OK;
+  if (n_host > nw->cap_rows) {
+    set_error("crl_net_forward: %d positions exceed the engine capacity %d", n_host, nw->cap_rows);
+    return CRL_EINVAL;
+  }
+  {
+    // the box may start at row n-1 for an odd n: rows beyond the map are zero-filled by the TMA unit
+    const int rows = planes == e->d_planes ? e->G : n_host;
+    if (planes != nw->planes_ptr || rows != nw->planes_rows) {
+      int rc = make_act_map(nw, &nw->map_planes, planes, 128, rows);
+      if (rc) return rc;
+      nw->planes_ptr = planes;
+      nw->planes_rows = rows;
+    }
+  }
+  int rc;
+  // stem: conv only (model.py:33-34 -- no BatchNorm / activation after it)
+  if ((rc = launch_conv(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0))) return rc;
+  for (int b = 0; b < 10; ++b) {
+    // x -> conv+BN+ReLU -> conv+BN -> +x -> ReLU  (model.py:111-122); the block output overwrites x in place
+    if ((rc = launch_conv(e, nw->map_act[0], 1 + 2 * b, n_dev, n_host, nullptr, nw->act[1], 1))) return rc;
+    if ((rc = launch_conv(e, nw->map_act[1], 2 + 2 * b, n_dev, n_host, nw->act[0], nw->act[0], 1))) return rc;
+  }
+  HeadParams hp;
+  hp.n_rows_dev = n_dev;
+  hp.n_rows_host = n_host;
+  hp.x = nw->act[0];
+  hp.w1x1 = nw->w1x1;
+  hp.s1x1 = nw->s1x1;
+  hp.wp = nw->wp;
+  hp.bp = nw->bp;
+  hp.wv1 = nw->wv1;
+  hp.bv1 = nw->bv1;
+  hp.wv2 = nw->wv2;
+  hp.bv2 = nw->bv2;
+  hp.policy = policy;
+  hp.value = value;
+  LaunchScope ls(e, KC_HEADS);
+  k_heads<<<div_up(n_host, HEAD_POS), HEAD_THREADS, HEAD_SMEM_BYTES, e->stream>>>(hp);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+// debug / test hook: one convolution layer on caller-provided activations (see tests/test_gpu_net.py)
+int net_debug_conv(crl_engine_impl* e, int layer, const __nv_bfloat16* in, int cin, int n, const __nv_bfloat16* residual,
+                   __nv_bfloat16* out, int relu) {
+  NetWeights* nw = e->net;
+  if (!nw || !nw->loaded) {
+    set_error("network weights are not loaded");
+    return CRL_ESTATE;
+  }
+  if (layer < 0 || layer >= N_CONVS || cin != nw->cin[layer]) {
+    set_error("crl_debug_conv: bad layer %d / cin %d", layer, cin);
+    return CRL_EINVAL;
+  }
+  CUtensorMap m;
+  int rc = make_act_map(nw, &m, in, cin, n);
+  if (rc) return rc;
+  return launch_conv(e, m, layer, nullptr, n, residual, out, relu);
+}
+
+}  // namespace crl

@@ -1,0 +1,171 @@
+/* chessrl_b200.h -- C ABI of libchessrl_b200.so, the B200-native lockstep self-play engine that stands in
+ * for the self-play hot path of AIRLegend/ChessRL.
+ *
+ * The reference has no FFI: its hot path sits behind Python classes whose arithmetic lives in python-chess
+ * and TensorFlow.  Each entry point below names the reference interface it replaces (file:line under
+ * /root/reference/src/chessrl); INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.  All compute runs in sm_100a CUDA kernels; there is no CPU path behind any of these calls.
+ *
+ * Conventions
+ *   - every function returns CRL_OK (0) or a negative crl_status; crl_last_error() gives the text.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors); "host" pointers are
+ *     ordinary host memory.  The library owns only what crl_create allocates.
+ *   - launches go to the cudaStream_t given at crl_create (pass torch's current stream); functions taking
+ *     only device pointers do not synchronise; functions with host pointers synchronise that stream.
+ *   - one engine per (process, GPU); calls on one handle are not re-entrant.
+ *
+ * Data formats
+ *   board record : 9 x uint64.  [0..5] pawns knights bishops rooks queens kings, [6] white, [7] black,
+ *                  [8] meta = turn(bit0,1=white) | castling KQkq(bits1-4) | ep+1(bits5-11) |
+ *                  halfmove(bits12-23) | fullmove(bits24-37) | ply=len(move_stack)(bits38-51) |
+ *                  reversible-run length(bits52-59).
+ *                  Device batches are structure-of-arrays: word k of board i at boards[k*n + i].
+ *                  Host batches (the *_host calls) are array-of-structures: board i at boards[9*i].
+ *   move word    : from | to<<6 | promo<<12 (promo 0 none, 1 N, 2 B, 3 R, 4 Q); 0xFFFF = no move.
+ *   planes       : bf16 [n][8][8][128], NHWC, row 0 = rank 8, channel order of netencoder.get_game_state,
+ *                  channel 127 = zero padding.
+ *   policy index : position in netencoder.get_uci_labels() (0..1967).
+ */
+#ifndef CHESSRL_B200_H
+#define CHESSRL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRL_RECORD_WORDS 9
+#define CRL_MAX_MOVES 256
+#define CRL_N_LABELS 1968
+#define CRL_PLANE_C 128
+#define CRL_RESULT_NONE 2
+#define CRL_MOVE_NONE 0xFFFF
+#define CRL_N_WEIGHT_TENSORS 140
+
+typedef enum {
+  CRL_OK = 0,
+  CRL_EINVAL = -1,   /* bad argument */
+  CRL_ECUDA = -2,    /* CUDA runtime / driver error */
+  CRL_ENOMEM = -3,   /* allocation failed or a node / edge pool overflowed */
+  CRL_ESTATE = -4    /* call order violated (e.g. simulate before begin_move, no weights loaded) */
+} crl_status;
+
+typedef struct crl_engine crl_engine;
+
+/* evaluator used by the tree search */
+#define CRL_EVAL_NET 0   /* the policy/value ResNet (model.py:31-63) on tcgen05 tensor cores            */
+#define CRL_EVAL_HASH 1  /* deterministic position-hash evaluator, bit-identical to                     */
+                         /* oracle/chessrl_oracle.py hash_evaluator -- for visit-count parity tests     */
+
+/* ---- lifecycle ---------------------------------------------------------------------------------- */
+/* max_games: lockstep lanes; max_nodes: tree nodes per game (>= sims per move + 1); avg_moves: edge-pool
+ * sizing hint (edges per game = max_nodes * avg_moves, 0 -> 64); stream: cudaStream_t or NULL. */
+int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, void* stream);
+int crl_destroy(crl_engine* e);
+const char* crl_last_error(void);
+int crl_version(void);
+
+/* ---- rules: python-chess behind game.Game ------------------------------------------------------- */
+/* Game.get_legal_moves (game.py:43-57): legal moves in python-chess generation order.
+ * moves_dev [n][CRL_MAX_MOVES], counts_dev [n], flags_dev [n] (bit0 in check, bit1 legal ep exists; may be NULL) */
+int crl_movegen(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* moves_dev, int32_t* counts_dev,
+                uint8_t* flags_dev);
+/* Board.push behind Game.move (game.py:28-41), no legality check; in place. moves_dev [n]; 0xFFFF = skip */
+int crl_make_moves(crl_engine* e, uint64_t* boards_dev, int n, const uint16_t* moves_dev);
+/* perft: each lane walks its own subtree depth-first; bulk != 0 counts the last ply without making moves */
+int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int bulk, uint64_t* nodes_dev);
+/* one breadth-first ply: children of board i are written at offsets_dev[i] (exclusive scan of counts).
+ * Call with out_dev == NULL to get counts only. */
+int crl_expand_frontier(crl_engine* e, const uint64_t* boards_dev, int n, const int64_t* offsets_dev,
+                        uint64_t* out_dev, int64_t out_n, int32_t* counts_dev);
+/* host-buffer convenience (AoS records): replay `n_moves` moves through Game.move semantics (illegal moves are
+ * rejected and skipped, game.py:37-41) and report what Game exposes.  Outputs may be NULL.
+ *   legal_host [CRL_MAX_MOVES], n_legal_host, result_host (Game.get_result, CRL_RESULT_NONE = None),
+ *   accepted_host [n_moves] (1 = move was legal and played), final_host [9] */
+int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
+                         uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host,
+                         uint8_t* accepted_host, uint64_t* final_host);
+
+/* ---- encoding: netencoder ------------------------------------------------------------------------- */
+/* netencoder.get_game_state (netencoder.py:72-91).  hist_dev: bitboards of the previous positions,
+ * word k of the i-th previous position of board b at hist_dev[((i*8)+k)*n + b], i = 0..7 (may be NULL);
+ * hist_len_dev [n]: how many of them exist (stack depth, clipped to 8; NULL = 0). */
+int crl_encode(crl_engine* e, const uint64_t* boards_dev, const uint64_t* hist_dev, const uint8_t* hist_len_dev,
+               int n, void* planes_bf16_dev);
+/* uci_dict lookup (agentdistributed.py:31-32,80-82): label index of every move; -1 for CRL_MOVE_NONE */
+int crl_policy_index(crl_engine* e, const uint16_t* moves_dev, const int32_t* counts_dev, int n,
+                     int16_t* idx_dev);
+/* copies the 64x64 (+ promotion) label table the kernels use: idx_host[promo*4096 + from*64 + to], promo 0..4
+ * (e may be NULL: the table is then produced without touching a device) */
+int crl_label_table_host(crl_engine* e, int16_t* idx_host);
+
+/* ---- network: model.ChessModel forward (model.py:31-63, 74-75, 111-122) ---------------------------- */
+/* weights_host: CRL_N_WEIGHT_TENSORS fp32 tensors in the order documented in DESIGN.md ("weight pack"),
+ * Keras layouts (conv HWIO, dense [in][out]); BatchNorm is folded on upload. */
+int crl_net_load_host(crl_engine* e, const float* const* weights_host, const int64_t* sizes, int n_tensors);
+/* planes_bf16_dev [n][8][8][128] -> policy_dev [n][1968] (softmax), value_dev [n] (tanh) */
+int crl_net_forward(crl_engine* e, const void* planes_bf16_dev, int n, float* policy_dev, float* value_dev);
+/* test hook: run convolution `layer` (0 = stem, 1..20 = residual tower) alone: in_dev [n][8][8][cin] bf16,
+ * optional residual_dev / out_dev [n][8][8][256] bf16 */
+int crl_debug_conv(crl_engine* e, int layer, const void* in_dev, int cin, int n, const void* residual_dev,
+                   void* out_dev, int relu);
+/* the deterministic test evaluator on raw boards (SoA), same outputs as the oracle's hash_evaluator */
+int crl_hash_eval(crl_engine* e, const uint64_t* boards_dev, int n, uint64_t seed, int policy_bits,
+                  float* policy_dev, float* value_dev);
+
+/* ---- lockstep games + tree search: selfplay.play_game / mctree.SelfPlayTree ------------------------ */
+int crl_set_evaluator(crl_engine* e, int kind, uint64_t seed, int policy_bits);
+/* load n games (slots first..first+n-1): start records (AoS host) and the moves already played
+ * (moves_host [n][stride], n_moves_host [n]); moves are replayed on the device so history planes and
+ * repetition keys exist.  Replaces Game(...) + Game.move replay (dataset.py:50-58). */
+int crl_games_set_host(crl_engine* e, int first, int n, const uint64_t* start_host, const uint16_t* moves_host,
+                       const int32_t* n_moves_host, int stride);
+/* per game: current record (AoS), plies played, Game.get_result (CRL_RESULT_NONE = running). NULLs allowed */
+int crl_games_get_host(crl_engine* e, int first, int n, uint64_t* boards_host, int32_t* plies_host,
+                       int8_t* results_host);
+/* the moves of one game so far (DatasetGame / Game.get_history 'moves') */
+int crl_game_moves_host(crl_engine* e, int game, uint16_t* moves_host, int cap, int32_t* n_host);
+/* AgentDistributed.best_move(real_game=True) (agentdistributed.py:56-58): policy argmax over legal moves for
+ * every game with mask_host[g] != 0 (NULL = all running games); writes picks_host [n_games] and plays them. */
+int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t* picks_host);
+/* Tree(root) (mctree.py:104-111): a fresh tree per running game rooted at its current position,
+ * root.visits = 1, root evaluated once for its children's priors. */
+int crl_mcts_begin_move(crl_engine* e);
+/* n_sims x SelfPlayTree.explore_tree (mctree.py:200-214) for every running game in lockstep.  inflight = 1 is
+ * the deterministic threads=1 schedule (the only one implemented in this round). */
+int crl_mcts_simulate(crl_engine* e, int n_sims, int inflight);
+/* root children in creation order (mctree.py:305-322 needs visits): arrays [n_games][CRL_MAX_MOVES] except
+ * n_children/root_visits/root_ply [n_games]; any may be NULL */
+int crl_mcts_root_stats_host(crl_engine* e, int32_t* child_visits, double* child_values, float* child_priors,
+                             uint16_t* child_moves, uint16_t* child_replies, int8_t* child_results,
+                             int32_t* n_children, int32_t* root_visits, double* root_values);
+/* search_move's return value (mctree.py:178-198) for pick_host[g] = index of the chosen root child
+ * (-1 = skip the game): out_moves_host [n_games][2] = (move_stack[-2], move_stack[-1]) of that child, then
+ * plays both through Game.move like selfplay.py:77-78 when `apply` != 0. */
+int crl_mcts_commit_host(crl_engine* e, const int32_t* pick_host, uint16_t* out_moves_host, int apply);
+/* flat dump of one game's tree for Node views / parity tests; arrays sized by `cap` nodes */
+typedef struct {
+  int32_t parent;      /* -1 for the root */
+  int32_t slot;        /* index among the parent's children (creation order) */
+  int32_t visits;
+  int32_t n_legal;     /* legal moves of the node's state */
+  int32_t n_children;  /* expanded so far */
+  int32_t result;      /* Game.get_result of the node's state, CRL_RESULT_NONE if not over */
+  uint16_t move;       /* our move leading here, 0xFFFF for the root */
+  uint16_t reply;      /* opponent reply, 0xFFFF if the game ended on our move */
+  float prior;
+  double value;        /* sum of backed-up values */
+  uint64_t board[9];   /* the node's state */
+} crl_node_host;
+int crl_mcts_node_dump_host(crl_engine* e, int game, crl_node_host* out, int cap, int32_t* n_host);
+/* counters since crl_create: [0] simulations, [1] net/hash evaluations requested, [2] kernels launched */
+int crl_counters_host(crl_engine* e, int64_t* out3);
+/* optional per-kernel-class timing (CUDA events on the engine stream); see DESIGN.md */
+int crl_profile(crl_engine* e, int enable);
+int crl_profile_read_host(crl_engine* e, double* ms_by_class, int64_t* launches_by_class, int n_classes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

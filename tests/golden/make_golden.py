@@ -34,7 +34,7 @@ FENS = {
     # mates / stalemates one ply away, to exercise terminal children and the (prev ply, our move) quirk
     "mate_in_1": "6k1/5ppp/8/8/8/8/5PPP/3R2K1 w - - 0 1",
     "kq_vs_k": "7k/8/5KQ1/8/8/8/8/8 w - - 0 1",
-    "black_to_move_mates": "6k1/5ppp/8/8/8/8/r4PPP/1r4K1 b - - 0 1",
+    "black_to_move_mates": "6k1/5ppp/8/8/8/1r6/r4PPP/6K1 b - - 0 1",
     "fifty_near": "8/8/4k3/8/8/3K4/R7/8 w - - 97 80",
     "ep_pin": "8/8/8/K2pP2r/8/8/8/4k3 w - d6 0 2",
 }

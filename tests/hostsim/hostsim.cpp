@@ -77,3 +77,156 @@ uint64_t hs_perft(const uint64_t* rec, int depth, int bulk) {
   return depth <= 0 ? 1 : perft_rec(b, depth, bulk);
 }
 }
+
+// ---- serial host run of the tree logic (tree_core.cuh) with the hash evaluator -----------------------
+#include "../../chessrl_b200/csrc/tree_core.cuh"
+#include "../../chessrl_b200/csrc/hash_eval.cuh"
+#include <stdlib.h>
+#include <vector>
+
+struct HostTree {
+  Pools P;
+  std::vector<int16_t> label_of;   // [5][64][64]
+  std::vector<float> policy;       // one row
+};
+
+extern "C" {
+
+void* hs_tree_new(int NN, int EA, const int16_t* label_of) {
+  HostTree* t = new HostTree();
+  Pools& P = t->P;
+  P.G = 1; P.NN = NN; P.EA = EA;
+  P.g_cur = (u64*)calloc(9, 8);
+  P.g_hist = (u64*)calloc(HIST_RING * 8, 8);
+  P.g_keys = (u64*)calloc(KEY_RING, 8);
+  P.g_moves = (u16*)calloc(MAX_GAME_PLIES, 2);
+  P.g_nmoves = (int*)calloc(1, 4);
+  P.g_result = (int8_t*)calloc(1, 1);
+  P.g_active = (u8*)calloc(1, 1);
+  P.nodes = (NodeRec*)calloc(NN, sizeof(NodeRec));
+  P.g_nnodes = (int*)calloc(1, 4);
+  P.g_nedges = (int*)calloc(1, 4);
+  P.e_move = (u16*)calloc(EA, 2);
+  P.e_prior = (float*)calloc(EA, 4);
+  P.e_visits = (int*)calloc(EA, 4);
+  P.e_value = (double*)calloc(EA, 8);
+  P.e_child = (int*)calloc(EA, 4);
+  P.e_result = (int8_t*)calloc(EA, 1);
+  P.r_visits = (int*)calloc(1, 4);
+  P.r_value = (double*)calloc(1, 8);
+  P.s_node = (int*)calloc(1, 4);
+  P.s_kind = (int*)calloc(1, 4);
+  P.s_moves = (u16*)calloc(MAX_MOVES, 2);
+  P.s_nmoves = (int*)calloc(1, 4);
+  P.s_row = (int*)calloc(1, 4);
+  P.eval_list = (int*)calloc(1, 4);
+  P.eval_n = (int*)calloc(1, 4);
+  P.err = (int*)calloc(1, 4);
+  P.counters = (long long*)calloc(4, 8);
+  t->label_of.assign(label_of, label_of + 5 * 4096);
+  t->policy.resize(1968);
+  return t;
+}
+
+// returns number of moves accepted
+int hs_game_set(void* h, const uint64_t* start, const uint16_t* moves, int n) {
+  HostTree* t = (HostTree*)h;
+  Pools& P = t->P;
+  for (int k = 0; k < 9; ++k) P.g_cur[k] = start[k];
+  P.g_nmoves[0] = 0;
+  game_refresh(P, 0, nullptr, nullptr);
+  int ok = 0;
+  for (int i = 0; i < n; ++i) ok += game_move(P, 0, moves[i]);
+  return ok;
+}
+int hs_game_move(void* h, uint16_t mv) { return game_move(((HostTree*)h)->P, 0, mv); }
+int hs_game_result(void* h) { return ((HostTree*)h)->P.g_result[0]; }
+
+static void host_eval(HostTree* t, const u64* rec, uint64_t seed, int bits, float* value) {
+  Board b = load_rec(rec);
+  u64 hh = eval_hash(b, seed);
+  for (int i = 0; i < 1968; ++i) t->policy[i] = hash_policy(hh, i, bits);
+  *value = hash_value(hh);
+}
+
+int hs_search(void* h, int sims, uint64_t seed, int bits) {
+  HostTree* t = (HostTree*)h;
+  Pools& P = t->P;
+  float v;
+  root_init(P, 0);
+  host_eval(t, P.nodes[0].p2, seed, bits, &v);
+  store_priors(P, 0, 0, t->policy.data(), t->label_of.data());
+  int evals = 1;
+  for (int s = 0; s < sims; ++s) {
+    int node, term;
+    select_descend(P, 0, [&](const NodeRec& n) { return best_edge_serial(P, 0, n); }, &node, &term);
+    double val;
+    if (term) {
+      val = (double)P.nodes[node].result;
+    } else {
+      int child;
+      int kind = expand_child(P, 0, node, &child);
+      node = child;
+      if (kind == KIND_NEED_REPLY) {
+        host_eval(t, P.nodes[child].p1, seed, bits, &v);
+        ++evals;
+        kind = reply_child(P, 0, child, t->policy.data(), t->label_of.data());
+      }
+      if (kind == KIND_EVAL_LEAF) {
+        host_eval(t, P.nodes[child].p2, seed, bits, &v);
+        ++evals;
+        store_priors(P, 0, child, t->policy.data(), t->label_of.data());
+        val = (double)v;
+      } else {
+        val = (double)P.nodes[child].result;
+      }
+    }
+    backup(P, 0, node, val);
+  }
+  return evals | (*P.err << 24);
+}
+
+// root stats in child creation order
+int hs_root_stats(void* h, int* visits, double* values, float* priors, uint16_t* moves, uint16_t* replies,
+                  int* results, int* root_visits, double* root_value) {
+  Pools& P = ((HostTree*)h)->P;
+  const NodeRec& r = P.nodes[0];
+  for (int k = 0; k < r.n_exp; ++k) {
+    visits[k] = P.e_visits[k];
+    values[k] = P.e_value[k];
+    priors[k] = P.e_prior[k];
+    const NodeRec& c = P.nodes[P.e_child[k]];
+    moves[k] = c.move;
+    replies[k] = c.reply;
+    results[k] = c.result;
+  }
+  *root_visits = P.r_visits[0];
+  *root_value = P.r_value[0];
+  return r.n_exp;
+}
+// visits of the children of root child k
+int hs_grandchild_visits(void* h, int k, int* visits) {
+  Pools& P = ((HostTree*)h)->P;
+  const NodeRec& c = P.nodes[P.e_child[k]];
+  for (int j = 0; j < c.n_exp; ++j) visits[j] = P.e_visits[c.edge0 + j];
+  return c.n_exp;
+}
+double hs_edge_score(int visits, double value, float prior, int child_result) {
+  return edge_score(visits, value, prior, child_result);
+}
+// planes of (node, which) via the history walk: out[9][8] bitboards, returns how many positions exist
+int hs_history(void* h, int node, int which, uint64_t* out) {
+  Pools& P = ((HostTree*)h)->P;
+  const NodeRec& n = P.nodes[node];
+  Board b = load_rec(which == 2 ? n.p2 : n.p1);
+  Cursor c{node, which, meta_ply(b.meta)};
+  int cnt = 0;
+  cursor_bitboards(P, 0, c, out);
+  cnt = 1;
+  while (cnt < 9 && cursor_prev(P, 0, c)) {
+    cursor_bitboards(P, 0, c, out + 8 * cnt);
+    ++cnt;
+  }
+  return cnt;
+}
+}

@@ -1,0 +1,168 @@
+"""CPU-side check of the DEVICE rule / tree code: chessrl_b200/csrc/{chess_core,tree_core,hash_eval}.cuh are
+compiled by g++ into a test-only harness (tests/hostsim) and compared with the oracle and the goldens.  This is
+what lets the kernels' arithmetic be validated in the GPU-less build container; the GPU tests repeat the same
+comparisons through the C ABI on the real kernels."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+import chessrl_oracle as O
+import hostsim
+from chessrl_b200 import boards as B
+
+chess = O.chess
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u16p = ctypes.POINTER(ctypes.c_uint16)
+i32p = ctypes.POINTER(ctypes.c_int)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    L = hostsim.load()
+    L.hs_tree_new.restype = ctypes.c_void_p
+    L.hs_tree_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int16)]
+    L.hs_game_set.argtypes = [ctypes.c_void_p, u64p, u16p, ctypes.c_int]
+    L.hs_search.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+    L.hs_root_stats.argtypes = [ctypes.c_void_p, i32p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float),
+                                u16p, u16p, i32p, i32p, ctypes.POINTER(ctypes.c_double)]
+    L.hs_grandchild_visits.argtypes = [ctypes.c_void_p, ctypes.c_int, i32p]
+    L.hs_edge_score.restype = ctypes.c_double
+    L.hs_edge_score.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_float, ctypes.c_int]
+    L.hs_history.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, u64p]
+    return L
+
+
+def movegen(lib, rec):
+    out = (ctypes.c_uint16 * 256)()
+    fl = (ctypes.c_int * 2)()
+    n = lib.hs_movegen(rec.ctypes.data_as(u64p), out, fl)
+    assert n >= 0
+    return [B.move_to_uci(out[i]) for i in range(n)], fl[0], fl[1]
+
+
+PERFT = [
+    (B.STARTING_FEN, [20, 400, 8902, 197281, 4865609]),
+    ("r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1", [48, 2039, 97862, 4085603]),
+    ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1", [14, 191, 2812, 43238, 674624]),
+    ("r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1", [6, 264, 9467, 422333]),
+    ("rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8", [44, 1486, 62379, 2103487]),
+    ("r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10", [46, 2079, 89890, 3894594]),
+]
+
+
+@pytest.mark.parametrize("fen,expected", PERFT)
+def test_device_core_perft(lib, fen, expected):
+    rec = B.record_from_fen(fen)
+    for d, e in enumerate(expected, 1):
+        assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 1) == e
+    assert lib.hs_perft(rec.ctypes.data_as(u64p), 3, 0) == expected[2]      # without leaf bulk counting
+
+
+def test_device_core_follows_oracle_along_games(lib, golden_dir):
+    cases = json.load(open(os.path.join(golden_dir, "rules.json")))["cases"]
+    checked = 0
+    for c in cases:
+        if c["fen"]:
+            ml, _, _ = movegen(lib, B.record_from_fen(c["fen"]))
+            assert ml == c["legal"], c["name"]
+            continue
+        rec, ob, keys = B.record_from_fen(), chess.Board(), []
+        for i, m in enumerate(c["moves"]):
+            lib.hs_make(rec.ctypes.data_as(u64p), B.uci_to_move(m))
+            ob.push(chess.Move.from_uci(m))
+            ml, chk, epl = movegen(lib, rec)
+            assert ml == [x.uci() for x in ob.generate_legal_moves()], (c["name"], i)
+            assert bool(chk) == ob.is_check() and bool(epl) == ob.has_legal_en_passant()
+            assert B.fen_from_record(rec, epl) == ob.fen()
+            k = lib.hs_key(rec.ctypes.data_as(u64p), epl)
+            keys.append(k)
+            rev = B.meta_fields(rec[8])["rev"]
+            reps = sum(1 for j in range(1, rev + 1) if len(keys) - 1 - j >= 0 and keys[len(keys) - 1 - j] == k)
+            res = lib.hs_result(rec.ctypes.data_as(u64p), len(ml), chk, reps)
+            assert (None if res == 2 else res) == O.OGame(board=ob).get_result(), (c["name"], i)
+            checked += 1
+    assert checked > 3000
+
+
+def _label_table():
+    tab = np.full((5, 64, 64), -1, dtype=np.int16)
+    for i, u in enumerate(O.uci_labels()):
+        m = B.uci_to_move(u)
+        tab[(m >> 12) & 7, m & 63, (m >> 6) & 63] = i
+    return tab
+
+
+def test_device_tree_core_matches_reference_mcts(lib, golden_dir):
+    tab = _label_table()
+    t = lib.hs_tree_new(1024, 1024 * 64, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    cases = json.load(open(os.path.join(golden_dir, "mcts_chess.json")))["cases"]
+    for c in cases:
+        rec = B.record_from_fen(c["fen"] or B.STARTING_FEN)
+        mv = np.array([B.uci_to_move(m) for m in c["moves"]], dtype=np.uint16)
+        assert lib.hs_game_set(t, rec.ctypes.data_as(u64p), mv.ctypes.data_as(u16p), len(mv)) == len(mv)
+        ev = lib.hs_search(t, c["sims"], c["eval_seed"], c["policy_bits"])
+        assert ev >> 24 == 0
+        V, W, Pr = (ctypes.c_int * 256)(), (ctypes.c_double * 256)(), (ctypes.c_float * 256)()
+        M, R, Rs = (ctypes.c_uint16 * 256)(), (ctypes.c_uint16 * 256)(), (ctypes.c_int * 256)()
+        rv, rw = ctypes.c_int(), ctypes.c_double()
+        n = lib.hs_root_stats(t, V, W, Pr, M, R, Rs, ctypes.byref(rv), ctypes.byref(rw))
+        kids = c["children"]
+        assert n == len(kids) and rv.value == c["root_visits"] and rw.value == float.fromhex(c["root_value"])
+        for k, kid in enumerate(kids):
+            line = [B.move_to_uci(M[k])] + ([B.move_to_uci(R[k])] if R[k] != 0xFFFF else [])
+            assert line == kid["line"]
+            assert V[k] == kid["visits"] and W[k] == float.fromhex(kid["value"])
+            assert (None if Rs[k] == 2 else Rs[k]) == kid["result"]
+            G = (ctypes.c_int * 256)()
+            ng = lib.hs_grandchild_visits(t, k, G)
+            assert [G[j] for j in range(ng)] == kid["grandchild_visits"]
+            if float.fromhex(kid["prior"]) != 1.0:
+                assert Pr[k] == float.fromhex(kid["prior"])
+                assert lib.hs_edge_score(V[k], W[k], Pr[k], Rs[k]) == float.fromhex(kid["score"])
+
+
+def test_device_history_walk_matches_planes(lib):
+    """The parent-chain walk used for history planes inside the tree reproduces the move-stack walk of
+    netencoder._get_game_history for a node deep in a search."""
+    tab = _label_table()
+    t = lib.hs_tree_new(256, 256 * 64, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    moves = ["e2e4", "e7e5", "g1f3", "b8c6", "f1b5"]
+    rec = B.record_from_fen()
+    mv = np.array([B.uci_to_move(m) for m in moves], dtype=np.uint16)
+    lib.hs_game_set(t, rec.ctypes.data_as(u64p), mv.ctypes.data_as(u16p), len(mv))
+    lib.hs_search(t, 120, 1, 24)
+    # oracle tree on the same game
+    g = O.OGame()
+    for m in moves:
+        g.move(m)
+    ot = O.OSelfPlayTree(g)
+    ot.search_move(O.OAgent(O.hash_evaluator(1, 24)), max_iters=120, noise=False)
+    # deepest oracle node, and the same node in the device tree by following creation order
+    node, path = ot.root, []
+    while node.children:
+        k = int(np.argmax([c.visits for c in node.children]))
+        path.append(k)
+        node = node.children[k]
+    # device node ids are creation-ordered per game; walk via grandchild bookkeeping is not exported, so compare the
+    # history of root children instead (they exercise tree + ring) and of the root itself
+    out = (ctypes.c_uint64 * 72)()
+    for k, child in enumerate(ot.root.children[:5]):
+        cnt = lib.hs_history(t, 1 + k, 2, out)       # root children are nodes 1.. in creation order
+        planes = O.planes(child.state)
+        got = np.zeros((8, 8, 127))
+        for s in range(cnt):
+            bb = [out[8 * s + j] for j in range(8)]
+            for ci, colour in ((0, 7), (7, 6)):
+                occ = bb[colour]
+                for sq in range(64):
+                    r, f = 7 - (sq >> 3), sq & 7
+                    if not (occ >> sq) & 1:
+                        got[r, f, 14 * s + ci] = 1
+                    for pt in range(6):
+                        if (bb[pt] & occ) >> sq & 1:
+                            got[r, f, 14 * s + ci + 1 + pt] = 1
+        got[:, :, 126] = 1.0 if child.state.turn else 0.0
+        assert (got == planes).all(), k
