@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- self-play MCTS simulations/sec (BASELINE.json's metric) for the lockstep engine on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--sims S] [--impl ours|reference]
+
+Workload (config.workload): BASELINE.json configs[3] "lockstep self-play 4,096 games x 200 sims/move on 1 B200",
+random-init ChessRL network, synthetic start/midgame positions (half the lanes advanced by 8-60 seeded random
+plies generated on the device).  With --gpus N (torchrun) every rank runs its own G games: games are independent,
+so the path shards by game with no data-path collective ("scaling": "weak").
+
+A STEP is one move search for all G lanes: a fresh tree per game, S simulations, i.e. G*S simulations.
+  value : simulations/s with the games resident in HBM (tree build + S lockstep simulations, CUDA events).
+  e2e   : the same metric through the public host API with HOST buffers inside the timed region: game records
+          host->device, search, root statistics device->host, the numpy move policy, picks host->device, the chosen
+          moves device->host (what selfplay.py does per move).
+  roofline     : the dominant kernel (tcgen05 3x3 convolution), algorithmic FLOPs / CUDA-event time inside the step,
+                 against the measured bf16 peak in MEASURED_PEAKS.json (sustained figure: timed inside a long step).
+  cpu_baseline : the oracle port of the reference path (python-chess restatement + mctree restatement + torch-CPU
+                 fp32 network, all host threads) on a bounded sample of the same workload; reported, not the target.
+  perft        : secondary metric of BASELINE.json (perft nodes/s over >= 65,536 lockstep boards), bit-exact totals.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONV_FLOP_PER_POS = 2 * (3 * 3 * 127 * 256 * 64 + 20 * 3 * 3 * 256 * 256 * 64)   # unpadded, SURVEY.md 8(d)
+NET_FLOP_PER_POS = 1548038656
+KIWI = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_games(engine, n_games, seed):
+    """Start positions for half the lanes, midgame positions (8-60 seeded random legal plies) for the rest.
+    The random plies are generated on the device with the engine's own movegen / make-move kernels."""
+    import torch
+    from chessrl_b200 import boards as B
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    target = torch.zeros(n_games, dtype=torch.int64)
+    half = n_games // 2
+    target[half:] = torch.randint(8, 61, (n_games - half,), generator=gen)
+    boards = engine.boards_to_device(np.tile(B.record_from_fen(), (n_games, 1)))
+    rnd = torch.randint(0, 1 << 30, (61, n_games), generator=gen).to(engine.device)
+    target_d = target.to(engine.device)
+    lists = torch.full((n_games, 60), B.MOVE_NONE - 65536, dtype=torch.int16, device=engine.device)
+    for ply in range(60):
+        moves, counts, _ = engine.movegen(boards)
+        alive = (counts > 0) & (target_d > ply)
+        idx = (rnd[ply] % counts.clamp(min=1)).to(torch.int64)
+        pick = moves.gather(1, idx[:, None])[:, 0]
+        pick = torch.where(alive, pick, torch.full_like(pick, -1))        # 0xFFFF = skip
+        engine.make_moves(boards, pick)
+        lists[:, ply] = pick
+        target_d = torch.where(alive, target_d, torch.zeros_like(target_d))   # a finished line stops
+    lists_h = lists.cpu().numpy().view(np.uint16)
+    move_lists = [[int(m) for m in row if m != B.MOVE_NONE] for row in lists_h]
+    start = np.tile(B.record_from_fen(), (n_games, 1))
+    return start, move_lists
+
+
+def perft_metric(engine):
+    """perft depth 5 from start + Kiwipete: BFS to >= 65,536 boards, then lockstep DFS per lane."""
+    import torch
+    from chessrl_b200 import boards as B
+    out = {}
+    total_nodes, total_ms = 0, 0.0
+    for name, fen, want in (("start", B.STARTING_FEN, 4865609), ("kiwipete", KIWI, 193690690)):
+        best = None
+        for rep in range(3):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
+            depth = 0
+            while frontier.shape[1] < 65536:
+                frontier, _ = engine.expand_frontier(frontier)
+                depth += 1
+            nodes = engine.perft(frontier, 5 - depth, bulk=True)
+            total = int(nodes.sum().item())
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            assert total == want, (name, total, want)
+            best = ms if best is None else min(best, ms)
+        out[name] = {"nodes": want, "ms": round(best, 3), "nodes_per_s": want / best * 1e3, "lanes": int(frontier.shape[1]),
+                     "leaf_bulk_counting": True}
+        total_nodes += want
+        total_ms += best
+    out["nodes_per_s"] = total_nodes / total_ms * 1e3
+    return out
+
+
+def cpu_reference_sims(budget_s, sims_per_move, seed=0):
+    """The reference path on the host cores: oracle restatement of selfplay.play_game / mctree (threads=1) with the
+    torch-CPU fp32 network, 1 game from the start position, `sims_per_move` simulations per move, for about
+    `budget_s` seconds.  Returns (simulations, seconds, evals, cores)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chessrl_oracle as O
+    import model_torch
+    from chessrl_b200 import model
+    torch.set_num_threads(os.cpu_count() or 1)
+    pack = model.random_pack(seed)
+
+    def evaluate(game):
+        with torch.no_grad():
+            p, v = model_torch.forward(pack, O.planes(game)[None].astype(np.float32), device="cpu")
+        return p[0].numpy(), np.float32(v[0].item())
+
+    agent = O.OAgent(evaluate)
+    game = O.OGame()
+    np.random.seed(seed)
+    sims = 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s and game.get_result() is None:
+        tree = O.OSelfPlayTree(game)
+        for _ in range(sims_per_move):
+            tree.explore_tree(agent)
+            sims += 1
+            if time.perf_counter() - t0 >= budget_s:
+                break
+        else:
+            pick = int(np.argmax(tree.compute_policy(tree.root, noise=True)))
+            stack = tree.root.children[pick].state.board.move_stack
+            if len(stack) >= 2:
+                game.move(str(stack[-2]))
+                game.move(str(stack[-1]))
+    dt = time.perf_counter() - t0
+    return sims, dt, agent.n_evals, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference_sims(min(per_step, 2.0), 100)
+    tot_s, tot_t, cores = 0, 0.0, 1
+    for _ in range(args.steps):
+        s, t, _, cores = cpu_reference_sims(per_step, 100)
+        tot_s += s
+        tot_t += t
+    v = tot_s / tot_t
+    sample = "1 game from the start position, 100 sims/move, threads=1 schedule, %.0f s of simulations per step" % per_step
+    line = {"impl": "reference", "metric": "mcts_simulations_per_sec", "value": v, "unit": "simulations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / max(1, args.steps) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD(args), "note": "reference arm = oracle port of python-chess + mctree + "
+                       "torch-CPU fp32 network (python-chess / TensorFlow are not installable offline)"},
+            "cpu_baseline": {"value": v, "unit": "simulations/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "simulations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def WORKLOAD(args):
+    return "lockstep self-play %d games/GPU x %d sims/move, random-init ChessRL net (BASELINE configs[3])" % (args.games, args.sims)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--games", type=int, default=4096, help="lockstep games per GPU")
+    ap.add_argument("--sims", type=int, default=200, help="simulations per move")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-perft", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from chessrl_b200 import boards as B
+    from chessrl_b200 import model
+    from chessrl_b200._lib import EVAL_NET
+    from chessrl_b200.engine import Engine
+    from chessrl_b200.lockstep import compute_policy
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+    G, S = args.games, args.sims
+
+    eng = Engine(max_games=G, max_nodes=S + 1, avg_moves=64)
+    pack = model.random_pack(seed=0)
+    if world > 1:
+        # weights live on rank 0 and are broadcast over NCCL (the only collective on this path besides timing)
+        flat = torch.cat([torch.from_numpy(w.reshape(-1)) for w in pack]).cuda()
+        dist.broadcast(flat, 0)
+        flat = flat.cpu().numpy()
+        o, pk = 0, []
+        for w in pack:
+            pk.append(flat[o:o + w.size].reshape(w.shape))
+            o += w.size
+        pack = pk
+    eng.load_weights(pack)
+    eng.set_evaluator(EVAL_NET)
+    start, move_lists = synthetic_games(eng, G, seed=1234 + rank)
+    eng.games_set(start, move_lists)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        eng.mcts_begin_move()
+        eng.mcts_simulate(S)
+
+    def e2e_step():
+        eng.games_set(start, move_lists)                                   # host -> device (records + move lists)
+        eng.mcts_begin_move()
+        eng.mcts_simulate(S)
+        st = eng.root_stats(want=("visits",))                              # device -> host
+        _, plies, results = eng.games_get(0, G)
+        picks = np.full(G, -1, dtype=np.int32)
+        for g in range(G):
+            k = int(st["n_children"][g])
+            if results[g] == B.RESULT_NONE and k:
+                picks[g] = int(np.argmax(compute_policy(st["visits"][g, :k], st["root_visits"][g], int(plies[g]), True)))
+        return eng.commit(picks, apply=False)                              # host -> device, device -> host
+
+    np.random.seed(0)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            flush.fill_(1)
+            fn()
+        barrier()
+        c0 = eng.counters()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)                                                 # L2 flush between timed iterations
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        c1 = eng.counters()
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, {k: c1[k] - c0[k] for k in c0}
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_dev, cnt_dev = timed(device_step, args.steps, args.warmup)
+    clocks = sampler.stop()
+    wall0 = time.perf_counter()
+    ms_e2e, cnt_e2e = timed(e2e_step, args.steps, max(1, min(args.warmup, 1)))
+    del wall0
+    sims_dev = cnt_dev["simulations"]
+    sims_e2e = cnt_e2e["simulations"]
+    if world > 1:
+        t = torch.tensor([sims_dev, sims_e2e, cnt_dev["launches"], cnt_dev["evaluations"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        sims_dev, sims_e2e, launches_all, evals_all = (float(x) for x in t.tolist())
+    else:
+        launches_all, evals_all = cnt_dev["launches"], cnt_dev["evaluations"]
+    value = sims_dev / (ms_dev * 1e-3)
+    e2e_value = sims_e2e / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (conv), measured live with CUDA events around every conv launch ----
+    roof = None
+    prof = None
+    if rank == 0:
+        eng.profile(True)
+        c0 = eng.counters()
+        eng.mcts_begin_move()
+        eng.mcts_simulate(min(S, 16))
+        torch.cuda.synchronize()
+        prof = eng.profile_read()
+        c1 = eng.counters()
+        eng.profile(False)
+        evals = c1["evaluations"] - c0["evaluations"]
+        conv = prof["conv"]
+        if conv["launches"] and conv["ms"] > 0:
+            flop_per_launch = evals * CONV_FLOP_PER_POS / conv["launches"]
+            t_launch = conv["ms"] * 1e-3 / conv["launches"]
+            achieved = flop_per_launch / t_launch / 1e12
+            roof = {"bound": "tensor", "kernel": "k_conv3x3 (tcgen05 implicit GEMM)", "achieved": achieved,
+                    "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
+                    "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                    "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6, "traffic": None,
+                    "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
+
+    # ---- perft (secondary metric) and CPU baseline, rank 0 only ----
+    perft = None
+    cpu = None
+    if rank == 0 and not args.no_perft:
+        small = Engine(max_games=1, max_nodes=8)
+        perft = perft_metric(small)
+        small.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        s, t, ev, cores = cpu_reference_sims(20.0, 100)
+        cpu = {"value": s / t, "unit": "simulations/s", "cores": cores, "kind": "port",
+               "sample": "1 game from the start position, 100 sims/move (BASELINE configs[0]), %d simulations / %d network "
+                         "evaluations in %.1f s; oracle port (python-chess restatement + mctree restatement + torch-CPU fp32 net)" % (s, ev, t)}
+
+    if rank == 0:
+        bytes_h2d = G * 72 + G * 4 + sum(len(m) for m in move_lists) * 2 + G * 4
+        bytes_d2h = G * 256 * 4 + 3 * G * 4 + G * 8 + G * 72 + G * 5 + G * 4
+        line = {
+            "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD(args), "games_per_gpu": G, "sims_per_move": S,
+                       "step": "one move search for all lanes = G*S simulations", "schedule": "1 in-flight simulation per game (exact threads=1 parity mode)",
+                       "l2": "256 MiB buffer written between timed steps; working set (trees + activations) > L2",
+                       "parallelism": "games sharded by lane across %d GPU(s), no per-simulation collective" % world},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "simulations/s", "h2d_bytes_per_step": bytes_h2d, "d2h_bytes_per_step": bytes_d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches_all),
+            "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
+            "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
+            "roofline": roof, "cpu_baseline": cpu, "perft": perft,
+        }
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

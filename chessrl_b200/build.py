@@ -44,7 +44,7 @@ def build(force=False, verbose=False):
         sys.stderr.write("\n".join(log))
     if failed:
         raise RuntimeError("nvcc failed; see chessrl_b200/build/nvcc.log")
-    cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-lcudart"]
+    cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     return OUT
 

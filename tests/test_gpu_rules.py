@@ -1,0 +1,159 @@
+"""GPU parity, rules: the CUDA movegen / make-move / perft kernels (through the C ABI) against the oracle,
+the golden move lists and the public perft table -- bit-exact, python-chess move ORDER included."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import chessrl_oracle as O
+from chessrl_b200 import boards as B
+
+pytestmark = pytest.mark.gpu
+chess = O.chess
+
+KIWI = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+PERFT5 = {B.STARTING_FEN: [20, 400, 8902, 197281, 4865609], KIWI: [48, 2039, 97862, 4085603, 193690690]}
+EXTRA = {
+    "8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1": [14, 191, 2812, 43238, 674624],
+    "r3k2r/Pppp1ppp/1b3nbN/nP6/BBP1P3/q4N2/Pp1P2PP/R2Q1RK1 w kq - 0 1": [6, 264, 9467, 422333],
+    "rnbq1k1r/pp1Pbppp/2p5/8/2B5/8/PPP1NnPP/RNBQK2R w KQ - 1 8": [44, 1486, 62379, 2103487],
+    "r4rk1/1pp1qppp/p1np1n2/2b1p1B1/2B1P1b1/P1NP1N2/1PP1QPPP/R4RK1 w - - 0 10": [46, 2079, 89890, 3894594],
+}
+
+
+def _moves_host(moves_t, counts_t):
+    mv = moves_t.cpu().numpy().view(np.uint16)
+    cn = counts_t.cpu().numpy()
+    return [[B.move_to_uci(m) for m in mv[i, :cn[i]]] for i in range(len(cn))]
+
+
+def _random_positions(n_games, plies, seed):
+    rng = random.Random(seed)
+    out = []
+    for _ in range(n_games):
+        b = chess.Board()
+        for _ in range(rng.randrange(1, plies)):
+            ms = list(b.generate_legal_moves())
+            if not ms:
+                break
+            b.push(rng.choice(ms))
+        out.append(b)
+    return out
+
+
+def test_movegen_golden_positions(engine1, golden_dir):
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "rules.json")))["cases"] if c["fen"]]
+    recs = np.stack([B.record_from_fen(c["fen"]) for c in cases])
+    mv, cn, fl = engine1.movegen(engine1.boards_to_device(recs))
+    got = _moves_host(mv, cn)
+    for c, g in zip(cases, got):
+        assert g == c["legal"], c["name"]
+
+
+def test_movegen_matches_oracle_on_random_positions(engine1):
+    boards = _random_positions(400, 120, seed=5)
+    recs = np.stack([B.record_from_fen(b.fen()) for b in boards])
+    # the FEN drops an ep square that is not capturable; restore the raw python-chess ep square in the record
+    for r, b in zip(recs, boards):
+        m = B.meta_fields(r[8])
+        r[8] = B.pack_meta(m["turn"], m["castle"], -1 if b.ep_square is None else b.ep_square, m["halfmove"], m["fullmove"])
+    mv, cn, fl = engine1.movegen(engine1.boards_to_device(recs))
+    got = _moves_host(mv, cn)
+    flags = fl.cpu().numpy()
+    for b, g, f in zip(boards, got, flags):
+        assert g == [m.uci() for m in b.generate_legal_moves()], b.fen()
+        assert bool(f & 1) == b.is_check() and bool(f & 2) == b.has_legal_en_passant()
+
+
+def test_make_moves_matches_oracle(engine1):
+    boards = _random_positions(200, 100, seed=6)
+    rng = random.Random(7)
+    recs, moves, after = [], [], []
+    for b in boards:
+        ms = list(b.generate_legal_moves())
+        if not ms:
+            continue
+        m = rng.choice(ms)
+        r = B.record_from_fen(b.fen())
+        f = B.meta_fields(r[8])
+        r[8] = B.pack_meta(f["turn"], f["castle"], -1 if b.ep_square is None else b.ep_square, f["halfmove"], f["fullmove"])
+        recs.append(r)
+        moves.append(B.uci_to_move(m.uci()))
+        b.push(m)
+        after.append(b)
+    t = engine1.boards_to_device(np.stack(recs))
+    mt = torch.from_numpy(np.array(moves, dtype=np.uint16).view(np.int16)).to(engine1.device)
+    engine1.make_moves(t, mt)
+    out = engine1.boards_to_host(t)
+    for r, b in zip(out, after):
+        f = B.meta_fields(r[8])
+        assert B.board_fen_from_record(r) == b.board_fen()
+        assert f["turn"] == b.turn and f["halfmove"] == b.halfmove_clock and f["fullmove"] == b.fullmove_number
+        assert f["ep"] == (-1 if b.ep_square is None else b.ep_square)
+        cr = b.clean_castling_rights()
+        want = (1 if cr & chess.BB_H1 else 0) | (2 if cr & chess.BB_A1 else 0) | (4 if cr & chess.BB_H8 else 0) | (8 if cr & chess.BB_A8 else 0)
+        assert f["castle"] == want and f["ply"] == 1
+
+
+@pytest.mark.parametrize("fen,expected", list(PERFT5.items()) + list(EXTRA.items()))
+def test_perft_single_lane(engine1, fen, expected):
+    t = engine1.boards_to_device(B.record_from_fen(fen)[None, :])
+    for d, e in enumerate(expected[:4], 1):
+        assert int(engine1.perft(t, d, bulk=True)[0]) == e
+    assert int(engine1.perft(t, 3, bulk=False)[0]) == expected[2]
+
+
+@pytest.mark.parametrize("fen", [B.STARTING_FEN, KIWI])
+def test_perft_depth5_lockstep_frontier(engine1, fen):
+    """BASELINE config 2: breadth-first to a frontier of >= 65,536 boards on the device, then every lane finishes
+    the remaining plies depth-first in lockstep; totals must equal the public perft(5) numbers."""
+    expected = PERFT5[fen]
+    frontier = engine1.boards_to_device(B.record_from_fen(fen)[None, :])
+    depth = 0
+    while frontier.shape[1] < 65536:
+        frontier, counts = engine1.expand_frontier(frontier)
+        depth += 1
+        assert frontier.shape[1] == expected[depth - 1]
+    nodes = engine1.perft(frontier, 5 - depth, bulk=True)
+    assert int(nodes.sum()) == expected[4]
+    nodes2 = engine1.perft(frontier, 5 - depth, bulk=False)
+    assert int(nodes2.sum()) == expected[4]
+
+
+def test_perft_replicated_65536_lanes(engine1):
+    """65,536 copies of the start position and Kiwipete run perft(3) in lockstep (pure lockstep throughput case)."""
+    for fen, want in ((B.STARTING_FEN, 8902), (KIWI, 97862)):
+        t = engine1.boards_to_device(np.tile(B.record_from_fen(fen), (65536, 1)))
+        nodes = engine1.perft(t, 3, bulk=True)
+        assert bool((nodes == want).all())
+
+
+def test_game_replay_semantics(engine1):
+    start = B.record_from_fen()
+    moves = [B.uci_to_move(m) for m in ["e2e4", "e7e5", "e2e5", "00000", "g1f3"]]
+    r = engine1.game_replay(start, moves)
+    assert list(r["accepted"]) == [True, True, False, False, True]          # Game.move rejects illegal / null moves
+    g = O.OGame()
+    for m in ["e2e4", "e7e5", "g1f3"]:
+        g.move(m)
+    assert [B.move_to_uci(m) for m in r["legal"]] == g.get_legal_moves() and r["result"] is None
+    # fool's mate: black wins -> -1
+    r = engine1.game_replay(start, [B.uci_to_move(m) for m in ["f2f3", "e7e5", "g2g4", "d8h4"]])
+    assert r["result"] == -1 and len(r["legal"]) == 0
+    # fivefold repetition through the device key ring
+    cyc = [B.uci_to_move(m) for m in ["g1f3", "g8f6", "f3g1", "f6g8"]]
+    assert engine1.game_replay(start, cyc * 3)["result"] is None
+    assert engine1.game_replay(start, cyc * 4)["result"] == 0
+
+
+def test_game_results_along_golden_games(engine1, golden_dir):
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "rules.json")))["cases"] if not c["fen"]]
+    for c in cases:
+        mv = [B.uci_to_move(m) for m in c["moves"]]
+        r = engine1.game_replay(B.record_from_fen(), mv)
+        assert r["accepted"].all() and r["result"] == c["final_result"], c["name"]
+        last = c["trace"][-1]
+        assert [B.move_to_uci(m) for m in r["legal"]] == last["legal"]

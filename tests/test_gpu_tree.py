@@ -1,0 +1,128 @@
+"""GPU parity, search: the lockstep PUCT kernels against golden vectors produced by the reference's own
+mctree.py (threads=1) -- visit counts, value sums, priors, PUCT scores, replies and returned moves, bit-exact,
+with the shared deterministic evaluator."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import chessrl_oracle as O
+from chessrl_b200 import boards as B
+from chessrl_b200._lib import EVAL_HASH
+from chessrl_b200.lockstep import LockstepSelfPlay, compute_policy
+
+pytestmark = pytest.mark.gpu
+chess = O.chess
+
+
+def _check_case(c, st, g, out_moves):
+    kids = c["children"]
+    n = int(st["n_children"][g])
+    assert n == len(kids), (c["name"], c["sims"], n, len(kids))
+    assert int(st["root_visits"][g]) == c["root_visits"]
+    assert float(st["root_values"][g]) == float.fromhex(c["root_value"])
+    for k, kid in enumerate(kids):
+        line = [B.move_to_uci(st["moves"][g, k])]
+        if st["replies"][g, k] != B.MOVE_NONE:
+            line.append(B.move_to_uci(st["replies"][g, k]))
+        assert line == kid["line"], (c["name"], k)
+        assert int(st["visits"][g, k]) == kid["visits"]
+        assert float(st["values"][g, k]) == float.fromhex(kid["value"])
+        r = int(st["results"][g, k])
+        assert (None if r == B.RESULT_NONE else r) == kid["result"]
+        if float.fromhex(kid["prior"]) != 1.0:
+            assert float(st["priors"][g, k]) == float.fromhex(kid["prior"])
+    pi = compute_policy(st["visits"][g, :n], st["root_visits"][g], len(c["moves"]), noise=False)
+    assert [float(x) for x in pi] == [float.fromhex(x) for x in c["policy_no_noise"]]
+    pick = int(np.argmax(pi))
+    return pick
+
+
+def test_mcts_golden_all_cases_in_lockstep(golden_dir):
+    """Every golden case sharing (evaluator seed, sims) runs in its own lane of ONE lockstep engine."""
+    from chessrl_b200.engine import Engine
+    cases = json.load(open(os.path.join(golden_dir, "mcts_chess.json")))["cases"]
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["eval_seed"], c["policy_bits"], c["sims"]), []).append(c)
+    for (seed, bits, sims), cs in groups.items():
+        e = Engine(max_games=len(cs), max_nodes=sims + 1, avg_moves=96)
+        e.set_evaluator(EVAL_HASH, seed, bits)
+        recs = np.stack([B.record_from_fen(c["fen"] or B.STARTING_FEN) for c in cs])
+        mls = [[B.uci_to_move(m) for m in c["moves"]] for c in cs]
+        e.games_set(recs, mls)
+        e.mcts_begin_move()
+        e.mcts_simulate(sims)
+        st = e.root_stats()
+        picks = np.full(len(cs), -1, dtype=np.int32)
+        for g, c in enumerate(cs):
+            picks[g] = _check_case(c, st, g, None)
+        out = e.commit(picks, apply=False)
+        for g, c in enumerate(cs):
+            assert [B.move_to_uci(out[g, 0]), B.move_to_uci(out[g, 1])] == c["returned"], (c["name"], sims)
+        cnt = e.counters()
+        assert cnt["simulations"] == sims * len(cs)
+        e.close()
+
+
+def test_node_dump_matches_oracle_tree(engine1):
+    g = O.OGame()
+    for m in ["d2d4", "g8f6", "c2c4", "e7e6"]:
+        g.move(m)
+    ot = O.OSelfPlayTree(g)
+    ot.search_move(O.OAgent(O.hash_evaluator(9, 24)), max_iters=150, noise=False)
+    engine1.set_evaluator(EVAL_HASH, 9, 24)
+    engine1.games_set(B.record_from_fen()[None, :], [[B.uci_to_move(m) for m in ["d2d4", "g8f6", "c2c4", "e7e6"]]])
+    engine1.mcts_begin_move()
+    engine1.mcts_simulate(150)
+    nodes = engine1.node_dump(0)
+    assert len(nodes) == 151
+    # rebuild parent -> children (creation order) and compare the whole tree shape with the oracle's
+    kids = {}
+    for i, n in enumerate(nodes):
+        if n.parent >= 0:
+            kids.setdefault(n.parent, []).append((n.slot, i))
+
+    def walk(onode, idx):
+        n = nodes[idx]
+        assert n.visits == onode.visits and n.value == float(onode.value)
+        ch = [i for _, i in sorted(kids.get(idx, []))]
+        assert len(ch) == len(onode.children)
+        for oc, ci in zip(onode.children, ch):
+            stack = [str(m) for m in oc.state.board.move_stack]
+            assert B.move_to_uci(nodes[ci].move) == stack[len(onode.state.board.move_stack)]
+            walk(oc, ci)
+    walk(ot.root, 0)
+
+
+def test_selfplay_golden_with_noise(golden_dir):
+    """selfplay.play_game loop incl. the Dirichlet draw (numpy legacy RNG, KAT-7) and the black-opens case."""
+    from chessrl_b200.engine import Engine
+    for run in json.load(open(os.path.join(golden_dir, "selfplay.json")))["runs"]:
+        e = Engine(max_games=1, max_nodes=run["sims"] + 1, avg_moves=96)
+        e.set_evaluator(EVAL_HASH, run["eval_seed"], 24)
+        sp = LockstepSelfPlay(e, sims=run["sims"], noise=True)
+        sp.start(colors=[run["player_color"]])
+        for k, (bm, am) in enumerate(run["picks"]):
+            np.random.seed(run["noise_seed_base"] + k)
+            out = sp.step()
+            assert [B.move_to_uci(out[0, 0]), B.move_to_uci(out[0, 1])] == [bm, am], (k, run["player_color"])
+        assert [B.move_to_uci(m) for m in e.game_moves(0)] == run["history"]["moves"]
+        e.close()
+
+
+def test_lockstep_lanes_are_independent():
+    """The same game in 64 lanes (plus different games in between) gives identical trees: no cross-lane state."""
+    from chessrl_b200.engine import Engine
+    e = Engine(max_games=64, max_nodes=81, avg_moves=96)
+    e.set_evaluator(EVAL_HASH, 4, 24)
+    recs = np.tile(B.record_from_fen(), (64, 1))
+    mls = [[B.uci_to_move(m) for m in (["e2e4", "c7c5"] if g % 2 else ["d2d4", "d7d5", "c2c4"])] for g in range(64)]
+    e.games_set(recs, mls)
+    e.mcts_begin_move()
+    e.mcts_simulate(80)
+    st = e.root_stats()
+    for g in range(2, 64):
+        assert (st["visits"][g] == st["visits"][g % 2]).all() and (st["values"][g] == st["values"][g % 2]).all()
+    e.close()
