@@ -1,0 +1,128 @@
+"""selfplay: drop-in for the reference's entry point (selfplay.py:111-167)
+
+    python -m chessrl_b200.selfplay modeldir [--games 1] [--threads 6] [--debug] [--sims 900] [--lanes N] [--no-train]
+
+Plays `--games` self-play games, appends them to <modeldir>/gameplays.json (README.md:77) and trains the model on
+them, saving the weights in place.  Unlike the reference, which plays one game at a time in a child process and
+talks to a prediction server over TCP, the games run in LOCKSTEP on the GPU (`--lanes` at a time, default all of
+them) and the "server" is the batched network evaluation inside the engine.  `--threads` is kept for
+compatibility (the search always uses the deterministic one-simulation-in-flight schedule); `--sims` exposes the
+reference's hard-coded 900 simulations per move (selfplay.py:76).  With torchrun the games are sharded by rank,
+rank 0 broadcasts the weights and gathers the finished games (NCCL); there is no per-simulation collective.
+"""
+
+from __future__ import annotations
+
+import argparse
+import os
+import random
+
+import numpy as np
+
+from . import boards as B
+from .agent import Agent
+from .dataset import DatasetGame
+from .game import Game
+from .lib.logger import Logger
+
+
+def get_model_path(directory):
+    """Newest <directory>/model-<n>.h5 by the reference's rule (selfplay.py:33-56); model-0.h5 if none."""
+    path = directory + "/model-0.h5"
+    models = [f for f in os.listdir(directory) if f.endswith("h5")]
+    if models:
+        max_v = max(m.split("-")[1] for m in models)
+        path = directory + "/" + [m for m in models if m.endswith(max_v)][0]
+    return path
+
+
+def play_game(agent, max_iters=900):
+    """One game through the single-object API, the reference's play_game loop (selfplay.py:59-84)."""
+    logger = Logger.get_instance()
+    player_color = random.random() >= 0.5
+    logger.debug("Player is white: %s" % player_color)
+    gam = Game(player_color=player_color)
+    agent.color = player_color
+    if player_color is False:
+        gam.move(agent.best_move(gam, real_game=True))
+    while gam.get_result() is None:
+        bm, am = agent.best_move(gam, real_game=False, ai_move=True, max_iters=max_iters)
+        if not gam.move(bm) | gam.move(am):
+            break                                   # the reference would spin forever on two rejected moves
+        logger.debug("\tMade move: %s" % bm)
+    logger.debug(gam.get_history())
+    return gam
+
+
+def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None):
+    """`n_games` games in lockstep; returns a DatasetGame.  The per-move host work is the numpy move policy only."""
+    from ._lib import EVAL_NET
+    from .engine import Engine
+    from .lockstep import LockstepSelfPlay
+    lanes = n_games if lanes is None else min(lanes, n_games)
+    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device)
+    eng.load_weights(model.weights)
+    eng.set_evaluator(EVAL_NET)
+    rng = random.Random(seed)
+    out = DatasetGame()
+    remaining = n_games
+    while remaining > 0:
+        n = min(lanes, remaining)
+        sp = LockstepSelfPlay(eng, n_games=n, sims=sims, noise=noise)
+        colors = [rng.random() >= 0.5 for _ in range(n)]
+        sp.start(colors=colors)
+        moves = 0
+        while sp.running().any() and (max_moves is None or moves < max_moves):
+            sp.step()
+            moves += 1
+        for g in range(n):
+            gm = Game(player_color=colors[g])
+            gm._sync(extra=[B.move_to_uci(m) for m in eng.game_moves(g)])
+            out.append(gm)
+        remaining -= n
+    eng.close()
+    return out
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser(description="Plays some chess games, stores the result and trains a model.")
+    parser.add_argument('model_dir', metavar='modeldir', help="where to store (and load from) the trained model and the logs")
+    parser.add_argument('--games', metavar='games', type=int, default=1)
+    parser.add_argument('--threads', metavar='threads', type=int, default=6)
+    parser.add_argument('--debug', action='store_true', default=False, help="Log debug messages on screen. Default false.")
+    parser.add_argument('--sims', type=int, default=900, help="MCTS simulations per move (reference: 900)")
+    parser.add_argument('--lanes', type=int, default=None, help="games stepped in lockstep per GPU")
+    parser.add_argument('--no-train', action='store_true', default=False)
+    args = parser.parse_args(argv)
+
+    logger = Logger.get_instance()
+    logger.set_level(0 if args.debug else 1)
+    os.makedirs(args.model_dir, exist_ok=True)
+    model_path = get_model_path(args.model_dir)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    torch.cuda.set_device(local_rank)
+    agent = Agent(True, weights=model_path if os.path.exists(model_path) else None)
+    if world > 1:
+        from . import sharding
+        sharding.init()
+        sharding.broadcast_weights(agent.model)
+    share = args.games // world + (1 if rank < args.games % world else 0)
+    logger.info("rank %d/%d plays %d game(s), %d simulations per move" % (rank, world, share, args.sims))
+    data = play_games_lockstep(agent.model, share, sims=args.sims, lanes=args.lanes, device=local_rank) if share else DatasetGame()
+    if world > 1:
+        from . import sharding
+        data = sharding.gather_games(data)
+    if rank == 0:
+        data.save(os.path.join(args.model_dir, "gameplays.json"))
+        if not args.no_train:
+            logger.info("Training on %d game(s)" % len(data))
+            agent.train(data, logdir=args.model_dir, epochs=1, validation_split=0, batch_size=1)
+            agent.save(model_path)
+
+
+if __name__ == "__main__":
+    main()

