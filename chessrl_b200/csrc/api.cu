@@ -3,6 +3,7 @@
 #include "engine.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace crl {
@@ -215,6 +216,20 @@ int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int a
   crl_engine* e = new crl_engine();
   e->device = device;
   e->stream = (cudaStream_t)stream;
+  if (e->stream == nullptr) {
+    // the legacy default stream cannot be captured into a CUDA graph: use an own BLOCKING stream, which keeps the
+    // implicit ordering with work the caller (torch) puts on the default stream
+    cudaError_t se = cudaStreamCreate(&e->stream);
+    if (se != cudaSuccess) {
+      delete e;
+      return cuda_fail(se, "cudaStreamCreate");
+    }
+    e->own_stream = true;
+  }
+  {
+    const char* g = getenv("CRL_NO_GRAPH");
+    e->use_graph = !(g && g[0] == '1');
+  }
   e->G = max_games;
   e->NN = max_nodes + 1;
   if (avg_moves <= 0) avg_moves = 64;
@@ -289,10 +304,12 @@ int crl_destroy(crl_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   drain_profile(e);
+  if (e->sim_graph) cudaGraphExecDestroy(e->sim_graph);
   net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_stage) cudaFree(e->d_stage);
   if (e->h_stage) cudaFreeHost(e->h_stage);
+  if (e->own_stream) cudaStreamDestroy(e->stream);
   delete e;
   return CRL_OK;
 }

@@ -52,6 +52,13 @@ struct crl_engine_impl {
   size_t h_stage_bytes = 0;
   void* d_stage = nullptr;
   size_t d_stage_bytes = 0;
+  // CUDA graph of one lockstep simulation (replayed n_sims times); rebuilt when the evaluator changes
+  bool own_stream = false;
+  bool use_graph = true;
+  cudaGraphExec_t sim_graph = nullptr;
+  unsigned long long sim_graph_key = 0;
+  long long sim_graph_launches = 0;
+  bool capturing = false;
   // accounting
   long long launches = 0;
   bool profiling = false;
@@ -77,14 +84,14 @@ struct LaunchScope {
   LaunchScope(crl_engine_impl* e_, int cls_, int n_launches = 1) : e(e_), cls(cls_) {
     e->launches += n_launches;
     e->prof_launches[cls] += n_launches;
-    if (e->profiling) {
+    if (e->profiling && !e->capturing) {
       cudaEventCreate(&a);
       cudaEventCreate(&b);
       cudaEventRecord(a, e->stream);
     }
   }
   ~LaunchScope() {
-    if (e->profiling) {
+    if (e->profiling && !e->capturing) {
       cudaEventRecord(b, e->stream);
       e->prof_pending.push_back({cls, {a, b}});
     }

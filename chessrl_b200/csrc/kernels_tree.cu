@@ -278,33 +278,81 @@ int tree_begin_move(crl_engine_impl* e, const u8* mask_dev) {
   return CRL_OK;
 }
 
-int tree_simulate(crl_engine_impl* e, int n_sims) {
-  for (int s = 0; s < n_sims; ++s) {
-    CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
-    use_list(e, 0);
-    {
-      LaunchScope ls(e, KC_TREE);
-      k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
-      CRL_CUDA(cudaGetLastError());
-    }
-    int rc = launch_eval_batch(e, 1);
-    if (rc != CRL_OK) return rc;
-    {
-      LaunchScope ls(e, KC_TREE);
-      k_reply<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
-                                                                       e->d_list[1], e->d_n + 1);
-      CRL_CUDA(cudaGetLastError());
-    }
-    use_list(e, 1);
-    rc = launch_eval_batch(e, 2);
-    if (rc != CRL_OK) return rc;
-    {
-      LaunchScope ls(e, KC_TREE);
-      k_finalize<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
-                                                                          e->d_label_of);
-      CRL_CUDA(cudaGetLastError());
-    }
+// one lockstep simulation of every running game: the fixed kernel sequence described at the top of this file
+static int one_simulation(crl_engine_impl* e) {
+  CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
+  use_list(e, 0);
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
+    CRL_CUDA(cudaGetLastError());
   }
+  int rc = launch_eval_batch(e, 1);
+  if (rc != CRL_OK) return rc;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_reply<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, e->d_list[1],
+                                                                     e->d_n + 1);
+    CRL_CUDA(cudaGetLastError());
+  }
+  use_list(e, 1);
+  rc = launch_eval_batch(e, 2);
+  if (rc != CRL_OK) return rc;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_finalize<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value, e->d_label_of);
+    CRL_CUDA(cudaGetLastError());
+  }
+  return CRL_OK;
+}
+
+// The sequence is identical for every simulation (batch sizes live in device memory), so it is captured once
+// into a CUDA graph and replayed: one graph launch instead of ~55 kernel launches per simulation.
+int tree_simulate(crl_engine_impl* e, int n_sims) {
+  if (n_sims <= 0) return CRL_OK;
+  const bool graph_ok = e->use_graph && !e->profiling && e->stream != nullptr;
+  if (!graph_ok) {
+    for (int s = 0; s < n_sims; ++s) {
+      int rc = one_simulation(e);
+      if (rc != CRL_OK) return rc;
+    }
+    return CRL_OK;
+  }
+  const unsigned long long key = 1ull + (unsigned long long)e->eval_kind + 2ull * (unsigned long long)e->eval_bits +
+                                 64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull);
+  if (e->sim_graph == nullptr || e->sim_graph_key != key) {
+    if (e->sim_graph) {
+      cudaGraphExecDestroy(e->sim_graph);
+      e->sim_graph = nullptr;
+    }
+    // run one simulation eagerly first: it creates whatever host-side state the launchers cache (tensor maps)
+    int rc = one_simulation(e);
+    if (rc != CRL_OK) return rc;
+    --n_sims;
+    const long long l0 = e->launches;
+    long long cls0[KC_COUNT];
+    for (int i = 0; i < KC_COUNT; ++i) cls0[i] = e->prof_launches[i];
+    cudaGraph_t graph = nullptr;
+    CRL_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    e->capturing = true;
+    rc = one_simulation(e);
+    e->capturing = false;
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    e->sim_graph_launches = e->launches - l0;
+    e->launches = l0;
+    for (int i = 0; i < KC_COUNT; ++i) e->prof_launches[i] = cls0[i];
+    if (rc != CRL_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+    ce = cudaGraphInstantiate(&e->sim_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
+    e->sim_graph_key = key;
+  }
+  for (int s = 0; s < n_sims; ++s) CRL_CUDA(cudaGraphLaunch(e->sim_graph, e->stream));
+  e->launches += (long long)n_sims * e->sim_graph_launches;
   return CRL_OK;
 }
 

@@ -26,6 +26,7 @@
 
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace crl {
@@ -434,6 +435,388 @@ __global__ void __launch_bounds__(HEAD_THREADS) k_heads(HeadParams p) {
 static constexpr int HEAD_SMEM_BYTES = (3 * 256 + HEAD_POS * (128 + 64 + 256 + CRL_N_LABELS)) * 4;
 
 // ======================================================================================================
+// v2: CTA-pair (cta_group::2) implicit-GEMM kernel.  Two CTAs of a cluster share one 256-row tile: each loads
+// its own 128 rows of A and HALF of the weight tile (128 of the 256 filters), so the weight traffic out of L2 per
+// SM is halved and a stage shrinks to 32 KB -> 6 stages (deeper TMA prefetch).  The leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256 across the pair, N=256, K=16); tcgen05.commit multicasts stage-release and
+// accumulator-ready to both CTAs; both CTAs run their own epilogue out of their own tensor memory.
+// The same kernel also runs plain GEMMs (taps = 1, A through a 2-D map) -- used for the policy head's dense layer --
+// and, for the last convolution, fuses the three 1x1 head convolutions (+BN+ReLU) into its epilogue.
+// ======================================================================================================
+static constexpr int V2_STAGES = 6;
+static constexpr int V2_A_BYTES = 128 * BLOCK_K * 2;      // 16 KB: this CTA's 128 rows
+static constexpr int V2_B_BYTES = 128 * BLOCK_K * 2;      // 16 KB: this CTA's half of the 256 filters
+static constexpr int V2_STAGE_BYTES = V2_A_BYTES + V2_B_BYTES;
+static constexpr int V2_SMEM_BYTES = 1024 + V2_STAGES * V2_STAGE_BYTES + 2 * TILE_N * 4 + 3 * 256 * 4 + 64 + 512;
+static constexpr uint32_t V2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TILE_N >> 3) << 17) | ((256u >> 4) << 24);
+static constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address
+
+struct ConvParams2 {
+  const int* n_units_dev;       // boards (conv) or rows (gemm) on the device, or null
+  int n_units_host;
+  int rows_per_unit;            // 64 for convolutions (squares per board), 1 for the dense GEMM
+  int taps;                     // 9 or 1
+  int k_chunks;                 // K per tap / 64
+  int n_tiles;                  // output tiles of 256 columns
+  const float* scale;           // [n_tiles*256]
+  const float* shift;           // [n_tiles*256]
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;           // bf16 [rows][256] (may be null when only the fused heads are wanted)
+  float* out_f32;               // gemm mode: fp32 [rows][out_ld]
+  int out_ld;
+  int relu;
+  // fused heads (last convolution only)
+  const float* head_w;          // [3][256]  policy ch0, policy ch1, value ch (1x1 conv kernels)
+  const float* head_s;          // [6]       folded scale x3, shift x3
+  __nv_bfloat16* pf_out;        // [boards][128] policy features, Keras flatten order (h*8+w)*2+c
+  float* vf_out;                // [boards][64]
+};
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// TMA loads of a CTA pair: the bytes are accounted on the LEADER's barrier
+__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                             int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once the issued MMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+k_conv_v2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, ConvParams2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + V2_STAGES * V2_A_BYTES;
+  float* s_scale = (float*)(smem + V2_STAGES * V2_STAGE_BYTES);
+  float* s_shift = s_scale + TILE_N;
+  float* s_hw = s_shift + TILE_N;               // [3][256]
+  float* s_hs = s_hw + 3 * 256;                 // [8]
+  uint64_t* bars = (uint64_t*)(s_hs + 16);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + V2_STAGES;
+  uint64_t* tmem_full = bars + 2 * V2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  int n_units = p.n_units_host;
+  if (p.n_units_dev) n_units = min(n_units, *p.n_units_dev);
+  const long long total_rows = (long long)n_units * p.rows_per_unit;
+  const int m_tiles = (int)((total_rows + 255) >> 8);
+  const int n_work = m_tiles * p.n_tiles;
+  const int n_kblocks = p.taps * p.k_chunks;
+  const bool fused_heads = p.head_w != nullptr;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+  }
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < V2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);        // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[i], 1);       // one multicast commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);    // 128 epilogue threads of each CTA arrive on the leader's barrier
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (fused_heads) {
+    for (int i = threadIdx.x; i < 3 * 256; i += CONV_THREADS) s_hw[i] = p.head_w[i];
+    if (threadIdx.x < 6) s_hs[threadIdx.x] = p.head_s[threadIdx.x];
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ================= TMA producer (one per CTA) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int w = pair; w < n_work; w += n_pairs) {
+      const int mt = w / p.n_tiles, nt = w - mt * p.n_tiles;
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * V2_STAGE_BYTES);
+        if (p.taps == 9) {
+          const int tap = kb / p.k_chunks, kc = kb - tap * p.k_chunks;
+          tma2_load_4d(smem_a + stage * V2_A_BYTES, &map_a, &full_bar[stage], kc * BLOCK_K, tap % 3 - 1, tap / 3 - 1,
+                       mt * 4 + (int)rank * 2);
+        } else {
+          tma2_load_2d(smem_a + stage * V2_A_BYTES, &map_a, &full_bar[stage], kb * BLOCK_K, mt * 256 + (int)rank * 128);
+        }
+        tma2_load_2d(smem_b + stage * V2_B_BYTES, &map_w, &full_bar[stage], kb * BLOCK_K, nt * TILE_N + (int)rank * 128);
+        if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
+        if (++stage == V2_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (threadIdx.x == 32 && rank == 0) {
+    // ================= MMA issuer (leader CTA only) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int w = pair; w < n_work; w += n_pairs, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * TILE_N;
+      for (int kb = 0; kb < n_kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * V2_A_BYTES));
+        const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * V2_B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC, (kb | k) != 0);
+        umma2_commit_both(&empty_bar[stage]);
+        if (kb == n_kblocks - 1) umma2_commit_both(&tmem_full[acc]);
+        if (++stage == V2_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    // the peer's epilogue threads arrive on OUR tmem_empty barriers: drain them before this CTA may exit
+    for (int a = 0; a < 2; ++a) {
+      const int used = (it + 1 - a) >> 1;           // accumulator a served iterations a, a+2, ...
+      if (used > 0) mbar_wait(&tmem_empty[a], (uint32_t)((used - 1) & 1));
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs, own tensor memory) =================
+    const int q = warp & 3;
+    const int row_in_cta = q * 32 + lane;
+    int it = 0;
+    for (int w = pair; w < n_work; w += n_pairs, ++it) {
+      const int mt = w / p.n_tiles, nt = w - mt * p.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      // the first tile of this CTA needs this layer's per-column constants; they are per n-tile
+      if (it == 0 || p.n_tiles > 1) {
+        // all 128 epilogue threads cooperate; named barrier 1 keeps the other warps out of it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 128; i < TILE_N; i += 128) {
+          s_scale[i] = p.scale[nt * TILE_N + i];
+          s_shift[i] = p.shift[nt * TILE_N + i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const long long grow = (long long)mt * 256 + rank * 128 + row_in_cta;
+      const bool valid = grow < total_rows;
+      __nv_bfloat16* orow = p.out ? p.out + grow * TILE_N : nullptr;
+      float* frow = p.out_f32 ? p.out_f32 + grow * p.out_ld + nt * TILE_N : nullptr;
+      const __nv_bfloat16* rrow = p.residual ? p.residual + grow * TILE_N : nullptr;
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * TILE_N + c0, v);
+        tmem_ld_wait();
+        if (!valid) continue;
+        uint4 res[4];
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + c0 + 8 * j);
+        }
+        float a[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t* rj = reinterpret_cast<const uint32_t*>(&res[j]);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              a[8 * j + 2 * h] += __uint_as_float(rj[h] << 16);
+              a[8 * j + 2 * h + 1] += __uint_as_float(rj[h] & 0xFFFF0000u);
+            }
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+        }
+        if (fused_heads) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            // the heads see the bf16-rounded trunk output, like every other consumer of an activation
+            const float x = __bfloat162float(__float2bfloat16_rn(a[j]));
+            h0 = fmaf(x, s_hw[c0 + j], h0);
+            h1 = fmaf(x, s_hw[256 + c0 + j], h1);
+            h2 = fmaf(x, s_hw[512 + c0 + j], h2);
+          }
+        }
+        if (orow) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(a[8 * j + 2 * h], a[8 * j + 2 * h + 1]);
+              pk[h] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        if (frow) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(frow + c0 + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive_remote(&tmem_empty[acc], 0);
+      if (fused_heads && valid) {
+        // row = board*64 + square: policy features in Keras flatten order (h*8+w)*2+c, value features [square]
+        const float f0 = fmaxf(h0 * s_hs[0] + s_hs[3], 0.f), f1 = fmaxf(h1 * s_hs[1] + s_hs[4], 0.f);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(f0, f1);
+        reinterpret_cast<__nv_bfloat162*>(p.pf_out)[grow] = b2;
+        p.vf_out[grow] = fmaxf(h2 * s_hs[2] + s_hs[5], 0.f);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// softmax over the policy logits + the value head's two dense layers; 8 positions per block, one warp each
+struct TailParams {
+  const int* n_rows_dev;
+  int n_rows_host;
+  const float* logits;   // [rows][ld]
+  int ld;
+  const float* vf;       // [rows][64]
+  const float* wv1;      // [64][256]
+  const float* bv1;      // [256]
+  const float* wv2;      // [256]
+  const float* bv2;      // [1]
+  float* policy;         // [rows][1968]
+  float* value;          // [rows]
+};
+__global__ void __launch_bounds__(256) k_softmax_value(TailParams p) {
+  __shared__ float s_vf[8][64];
+  __shared__ float s_hid[8][256];
+  int n_rows = p.n_rows_host;
+  if (p.n_rows_dev) n_rows = min(n_rows, *p.n_rows_dev);
+  const int pos0 = blockIdx.x * 8;
+  if (pos0 >= n_rows) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * 64; i += 256) {
+    const int q = i >> 6;
+    s_vf[q][i & 63] = (pos0 + q < n_rows) ? p.vf[(long long)(pos0 + q) * 64 + (i & 63)] : 0.f;
+  }
+  __syncthreads();
+  {
+    const int j = threadIdx.x;
+    float acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+    for (int i = 0; i < 64; ++i) {
+      const float w = p.wv1[i * 256 + j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc[q] = fmaf(s_vf[q][i], w, acc[q]);
+    }
+    const float b = p.bv1[j];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s_hid[q][j] = fmaxf(acc[q] + b, 0.f);
+  }
+  __syncthreads();
+  const int pos = pos0 + warp;
+  if (pos >= n_rows) return;
+  const float* lg = p.logits + (long long)pos * p.ld;
+  float x[62];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 62; ++k) {
+    const int j = lane + 32 * k;
+    x[k] = j < CRL_N_LABELS ? lg[j] : -INFINITY;
+    m = fmaxf(m, x[k]);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 62; ++k) {
+    x[k] = expf(x[k] - m);
+    s += x[k];
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  const float inv = 1.0f / s;
+  float* out = p.policy + (long long)pos * CRL_N_LABELS;
+#pragma unroll
+  for (int k = 0; k < 62; ++k) {
+    const int j = lane + 32 * k;
+    if (j < CRL_N_LABELS) out[j] = x[k] * inv;
+  }
+  float v = 0.f;
+  for (int j = lane; j < 256; j += 32) v = fmaf(s_hid[warp][j], p.wv2[j], v);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) p.value[pos] = tanhf(v + p.bv2[0]);
+}
+
+// ======================================================================================================
 // host side: weight pack, tensor maps, forward
 // ======================================================================================================
 static constexpr int N_CONVS = 21;
@@ -460,6 +843,16 @@ struct NetWeights {
         *wv2 = nullptr, *bv2 = nullptr;
   PFN_encodeTiled encode = nullptr;
   int n_sms = 148;
+  // v2 (CTA-pair kernel, fused heads)
+  bool use_v2 = true;
+  CUtensorMap map_w2[N_CONVS];              // weight boxes of 128 filters (one CTA's half)
+  __nv_bfloat16* pf = nullptr;              // [cap][128] policy features (bf16)
+  float* vf = nullptr;                      // [cap][64] value features
+  float* logits = nullptr;                  // [cap][2048] policy logits
+  __nv_bfloat16* wp_bf16 = nullptr;         // [2048][128] policy dense kernel, K-major, zero padded
+  float* bp_pad = nullptr;                  // [2048]
+  float* ones = nullptr;                    // [2048]
+  CUtensorMap map_pf, map_wp;
 };
 
 static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int cin, int rows) {
@@ -476,10 +869,11 @@ static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int 
   }
   return CRL_OK;
 }
-static int make_w_map(NetWeights* nw, CUtensorMap* map, const void* base, int k_total) {
-  cuuint64_t dims[2] = {(cuuint64_t)k_total, TILE_N};
+static int make_w_map(NetWeights* nw, CUtensorMap* map, const void* base, int k_total, int n_rows = TILE_N,
+                      int box_n = TILE_N) {
+  cuuint64_t dims[2] = {(cuuint64_t)k_total, (cuuint64_t)n_rows};
   cuuint64_t strides[1] = {(cuuint64_t)k_total * 2};
-  cuuint32_t box[2] = {BLOCK_K, TILE_N};
+  cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)box_n};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = nw->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -525,6 +919,20 @@ int net_create(crl_engine_impl* e) {
     if ((rc = dev_alloc(e, &nw->scale[i], 256))) return rc;
     if ((rc = dev_alloc(e, &nw->shift[i], 256))) return rc;
     if ((rc = make_w_map(nw, &nw->map_w[i], nw->w[i], 9 * nw->cin[i]))) return rc;
+    if ((rc = make_w_map(nw, &nw->map_w2[i], nw->w[i], 9 * nw->cin[i], TILE_N, 128))) return rc;
+  }
+  {
+    const char* v1 = getenv("CRL_CONV_V1");
+    nw->use_v2 = !(v1 && v1[0] == '1');
+    if ((rc = dev_alloc(e, &nw->pf, (size_t)(nw->cap_rows + 256) * 128))) return rc;
+    if ((rc = dev_alloc(e, &nw->vf, (size_t)(nw->cap_rows + 256) * 64))) return rc;
+    if ((rc = dev_alloc(e, &nw->logits, (size_t)(nw->cap_rows + 256) * 2048))) return rc;
+    if ((rc = dev_alloc(e, &nw->wp_bf16, (size_t)2048 * 128))) return rc;
+    if ((rc = dev_alloc(e, &nw->bp_pad, 2048))) return rc;
+    if ((rc = dev_alloc(e, &nw->ones, 2048))) return rc;
+    CRL_CUDA(cudaMemsetAsync(nw->pf, 0, (size_t)(nw->cap_rows + 256) * 128 * 2, e->stream));
+    if ((rc = make_w_map(nw, &nw->map_pf, nw->pf, 128, nw->cap_rows + 256, 128))) return rc;
+    if ((rc = make_w_map(nw, &nw->map_wp, nw->wp_bf16, 128, 2048, 128))) return rc;
   }
   for (int i = 0; i < 2; ++i) {
     if ((rc = dev_alloc(e, &nw->act[i], (size_t)nw->cap_rows * 64 * 256))) return rc;
@@ -541,6 +949,7 @@ int net_create(crl_engine_impl* e) {
   if ((rc = dev_alloc(e, &nw->bv2, 1))) return rc;
   CRL_CUDA(cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_BYTES));
+  CRL_CUDA(cudaFuncSetAttribute(k_conv_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
   return CRL_OK;
 }
 
@@ -643,6 +1052,18 @@ int net_load(crl_engine_impl* e, const float* const* w, const int64_t* sizes, in
   CRL_CUDA(cudaMemcpyAsync(nw->bv1, w[V0 + 7], 256 * 4, cudaMemcpyHostToDevice, e->stream));
   CRL_CUDA(cudaMemcpyAsync(nw->wv2, w[V0 + 8], 256 * 4, cudaMemcpyHostToDevice, e->stream));
   CRL_CUDA(cudaMemcpyAsync(nw->bv2, w[V0 + 9], 4, cudaMemcpyHostToDevice, e->stream));
+  {
+    std::vector<uint16_t> wpt((size_t)2048 * 128, 0);
+    std::vector<float> bpad(2048, 0.f), one(2048, 1.f);
+    for (int j = 0; j < CRL_N_LABELS; ++j) {
+      bpad[j] = w[P0 + 7][j];
+      for (int i = 0; i < 128; ++i) wpt[(size_t)j * 128 + i] = f2bf(w[P0 + 6][(size_t)i * CRL_N_LABELS + j]);
+    }
+    CRL_CUDA(cudaMemcpyAsync(nw->wp_bf16, wpt.data(), wpt.size() * 2, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaMemcpyAsync(nw->bp_pad, bpad.data(), 2048 * 4, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaMemcpyAsync(nw->ones, one.data(), 2048 * 4, cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaStreamSynchronize(e->stream));
+  }
   CRL_CUDA(cudaStreamSynchronize(e->stream));
   nw->loaded = true;
   return CRL_OK;
@@ -665,6 +1086,78 @@ static int launch_conv(crl_engine_impl* e, const CUtensorMap& map_in, int L, con
   if (grid < 1) grid = 1;
   LaunchScope ls(e, KC_CONV);
   k_conv3x3<<<grid, CONV_THREADS, CONV_SMEM_BYTES, e->stream>>>(map_in, nw->map_w[L], p);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+static int launch_conv_v2(crl_engine_impl* e, const CUtensorMap& map_in, int L, const int* n_dev, int n_host,
+                          const __nv_bfloat16* residual, __nv_bfloat16* out, int relu, bool fuse_heads) {
+  NetWeights* nw = e->net;
+  ConvParams2 p;
+  memset(&p, 0, sizeof(p));
+  p.n_units_dev = n_dev;
+  p.n_units_host = n_host;
+  p.rows_per_unit = 64;
+  p.taps = 9;
+  p.k_chunks = nw->cin[L] / BLOCK_K;
+  p.n_tiles = 1;
+  p.scale = nw->scale[L];
+  p.shift = nw->shift[L];
+  p.residual = residual;
+  p.out = out;
+  p.relu = relu;
+  if (fuse_heads) {
+    p.head_w = nw->w1x1;
+    p.head_s = nw->s1x1;
+    p.pf_out = nw->pf;
+    p.vf_out = nw->vf;
+  }
+  int work = (n_host + 3) / 4;
+  int pairs = work < nw->n_sms / 2 ? work : nw->n_sms / 2;
+  if (pairs < 1) pairs = 1;
+  LaunchScope ls(e, KC_CONV);
+  k_conv_v2<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(map_in, nw->map_w2[L], p);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+
+// policy dense layer (128 -> 1968, zero padded to 2048) as a tcgen05 GEMM, then softmax + value head
+static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, float* policy, float* value) {
+  NetWeights* nw = e->net;
+  ConvParams2 p;
+  memset(&p, 0, sizeof(p));
+  p.n_units_dev = n_dev;
+  p.n_units_host = n_host;
+  p.rows_per_unit = 1;
+  p.taps = 1;
+  p.k_chunks = 2;
+  p.n_tiles = 8;
+  p.scale = nw->ones;
+  p.shift = nw->bp_pad;
+  p.out_f32 = nw->logits;
+  p.out_ld = 2048;
+  int work = ((n_host + 255) / 256) * 8;
+  int pairs = work < nw->n_sms / 2 ? work : nw->n_sms / 2;
+  if (pairs < 1) pairs = 1;
+  {
+    LaunchScope ls(e, KC_HEADS);
+    k_conv_v2<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_pf, nw->map_wp, p);
+    CRL_CUDA(cudaGetLastError());
+  }
+  TailParams t;
+  t.n_rows_dev = n_dev;
+  t.n_rows_host = n_host;
+  t.logits = nw->logits;
+  t.ld = 2048;
+  t.vf = nw->vf;
+  t.wv1 = nw->wv1;
+  t.bv1 = nw->bv1;
+  t.wv2 = nw->wv2;
+  t.bv2 = nw->bv2;
+  t.policy = policy;
+  t.value = value;
+  LaunchScope ls(e, KC_HEADS);
+  k_softmax_value<<<div_up(n_host, 8), 256, 0, e->stream>>>(t);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }
@@ -692,6 +1185,16 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     }
   }
   int rc;
+  if (nw->use_v2) {
+    if ((rc = launch_conv_v2(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0, false))) return rc;
+    for (int b = 0; b < 10; ++b) {
+      if ((rc = launch_conv_v2(e, nw->map_act[0], 1 + 2 * b, n_dev, n_host, nullptr, nw->act[1], 1, false))) return rc;
+      const bool last = b == 9;   // the last convolution feeds only the heads: fuse them, skip the activation write
+      if ((rc = launch_conv_v2(e, nw->map_act[1], 2 + 2 * b, n_dev, n_host, nw->act[0], last ? nullptr : nw->act[0], 1, last)))
+        return rc;
+    }
+    return launch_heads_v2(e, n_dev, n_host, policy, value);
+  }
   // stem: conv only (model.py:33-34 -- no BatchNorm / activation after it)
   if ((rc = launch_conv(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0))) return rc;
   for (int b = 0; b < 10; ++b) {
@@ -734,6 +1237,7 @@ int net_debug_conv(crl_engine_impl* e, int layer, const __nv_bfloat16* in, int c
   CUtensorMap m;
   int rc = make_act_map(nw, &m, in, cin, n);
   if (rc) return rc;
+  if (nw->use_v2) return launch_conv_v2(e, m, layer, nullptr, n, residual, out, relu, false);
   return launch_conv(e, m, layer, nullptr, n, residual, out, relu);
 }
 
