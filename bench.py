@@ -145,8 +145,16 @@ def perft_metric(engine):
             ms = a.elapsed_time(b)
             assert total == want, (name, total, want)
             best = ms if best is None else min(best, ms)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        nodes_nb = engine.perft(frontier, 5 - depth, bulk=False)
+        b.record()
+        torch.cuda.synchronize()
+        assert int(nodes_nb.sum().item()) == want
         out[name] = {"nodes": want, "ms": round(best, 3), "nodes_per_s": want / best * 1e3, "lanes": int(frontier.shape[1]),
-                     "leaf_bulk_counting": True}
+                     "leaf_bulk_counting": True, "headline": "with leaf bulk counting, frontier expansion included",
+                     "dfs_only_no_bulk_nodes_per_s": want / a.elapsed_time(b) * 1e3}
         total_nodes += want
         total_ms += best
     out["nodes_per_s"] = total_nodes / total_ms * 1e3
@@ -355,10 +363,14 @@ def main():
             flop_per_launch = evals * CONV_FLOP_PER_POS / conv["launches"]
             t_launch = conv["ms"] * 1e-3 / conv["launches"]
             achieved = flop_per_launch / t_launch / 1e12
-            roof = {"bound": "tensor", "kernel": "k_conv3x3 (tcgen05 implicit GEMM)", "achieved": achieved,
+            roof = {"bound": "tensor", "kernel": "k_conv_v2 (tcgen05 cta_group::2 implicit-GEMM 3x3 convolution)", "achieved": achieved,
                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
-                    "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6, "traffic": None,
+                    "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4,096 positions, mean of 4 captured
+                    # launches (profiles/r01_ncu_conv_v2.txt); algorithmic: 134 MB in + 134 MB out (+134 MB residual on every
+                    # second layer) + 1.2 MB weights -- the write-back of the last wave is still in L2 when the launch ends
+                    "traffic": 288.3e6 if G == 4096 else None, "traffic_unit": "bytes/launch",
                     "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 
     # ---- perft (secondary metric) and CPU baseline, rank 0 only ----

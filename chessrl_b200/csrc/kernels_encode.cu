@@ -23,34 +23,44 @@ struct EncShared {
   int turn;
 };
 
-// all threads of the block write the 64 x 128 plane tile of one position
-__device__ __forceinline__ void write_planes(const EncShared& s, __nv_bfloat16* __restrict__ out) {
+// All threads of the block write the 64 x 128 plane tile of one position.
+// Step 1: one thread per square folds the 9 states into a 128-bit channel mask (14 bits per state: "no black piece",
+// six black piece bits, "no white piece", six white piece bits; bit 126 = side to move).  Step 2: all threads expand
+// mask bytes to bf16 and store 16 bytes each, 2 KB contiguous per block-wide store -- the kernel is then bound by the
+// 16 KB it writes per position, not by bit fiddling.
+__device__ __forceinline__ void write_planes(const EncShared& s, unsigned (*s_mask)[4],
+                                             __nv_bfloat16* __restrict__ out) {
+  if (threadIdx.x < 64) {
+    const int cell = threadIdx.x;
+    const int sq = (7 - (cell >> 3)) * 8 + (cell & 7);
+    u64 lo = 0, hi = 0;
+    for (int st = 0; st < s.avail; ++st) {
+      const unsigned ob = (unsigned)((s.bb[st][OCC_B] >> sq) & 1), ow = (unsigned)((s.bb[st][OCC_W] >> sq) & 1);
+      unsigned pt = 0;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) pt |= (unsigned)((s.bb[st][k] >> sq) & 1) << k;
+      const u64 m14 = (u64)((ob ^ 1u) | ((ob ? pt : 0u) << 1) | ((ow ^ 1u) << 7) | ((ow ? pt : 0u) << 8));
+      const int o = 14 * st;
+      if (o < 64) {
+        lo |= m14 << o;
+        if (o > 50) hi |= m14 >> (64 - o);
+      } else {
+        hi |= m14 << (o - 64);
+      }
+    }
+    hi |= (u64)(s.turn & 1) << 62;   // channel 126
+    s_mask[cell][0] = (unsigned)lo;
+    s_mask[cell][1] = (unsigned)(lo >> 32);
+    s_mask[cell][2] = (unsigned)hi;
+    s_mask[cell][3] = (unsigned)(hi >> 32);
+  }
+  __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(out);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int id = j * ENC_THREADS + threadIdx.x;   // 16-byte chunk id: 64 squares x 16 chunks
+    const int id = j * ENC_THREADS + threadIdx.x;   // 16-byte chunk id: 64 squares x 16 chunks of 8 channels
     const int cell = id >> 4, chunk = id & 15;
-    const int h = cell >> 3, w = cell & 7;
-    const int sq = (7 - h) * 8 + w;
-    unsigned bits = 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-      const int c = chunk * 8 + t;
-      unsigned v = 0;
-      if (c < 126) {
-        const int st = c / 14, k = c - st * 14;
-        if (st < s.avail) {
-          const int white = k >= 7;
-          const int kk = white ? k - 7 : k;
-          const u64 side = s.bb[st][white ? OCC_W : OCC_B];
-          if (kk == 0) v = ((side >> sq) & 1) ? 0u : 1u;
-          else v = (unsigned)(((s.bb[st][kk - 1] & side) >> sq) & 1);
-        }
-      } else if (c == 126) {
-        v = (unsigned)s.turn;
-      }
-      bits |= v << t;
-    }
+    const unsigned bits = (s_mask[cell][chunk >> 2] >> ((chunk & 3) * 8)) & 0xFFu;
     uint4 q;
     q.x = ((bits & 1) ? 0x3F80u : 0u) | ((bits & 2) ? 0x3F800000u : 0u);
     q.y = ((bits & 4) ? 0x3F80u : 0u) | ((bits & 8) ? 0x3F800000u : 0u);
@@ -66,6 +76,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_boards(const u64* __rest
                                                                const u8* __restrict__ hist_len, int n,
                                                                __nv_bfloat16* __restrict__ planes) {
   __shared__ EncShared s;
+  __shared__ unsigned s_mask[64][4];
   const int i = blockIdx.x;
   if (threadIdx.x < 72) {
     const int st = threadIdx.x >> 3, k = threadIdx.x & 7;
@@ -80,13 +91,14 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_boards(const u64* __rest
     }
   }
   __syncthreads();
-  write_planes(s, planes + (long long)i * 64 * 128);
+  write_planes(s, s_mask, planes + (long long)i * 64 * 128);
 }
 
 // tree / game batches: row r -> game eval_list[r]; position = (s_node[g], which) or the root when which==0
 __global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
                                                              __nv_bfloat16* __restrict__ planes) {
   __shared__ EncShared s;
+  __shared__ unsigned s_mask[64][4];
   const int r = blockIdx.x;
   if (r >= *P.eval_n) return;
   const int g = P.eval_list[r];
@@ -106,7 +118,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
     s.turn = (int)(meta & 1);
   }
   __syncthreads();
-  write_planes(s, planes + (long long)r * 64 * 128);
+  write_planes(s, s_mask, planes + (long long)r * 64 * 128);
 }
 
 __global__ void k_policy_index(const u16* __restrict__ moves, const int* __restrict__ counts, int n,

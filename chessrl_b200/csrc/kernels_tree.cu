@@ -78,45 +78,80 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
   }
 }
 
-// rows of batch A (positions after our move) -> opponent reply, node state, batch B
+// rows of batch A (positions after our move) -> opponent reply, node state, batch B.
+// One WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
+// (agentdistributed.py:56-58); lane 0 then plays the reply and builds the node.
 __global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __restrict__ policy,
                                                       const int16_t* __restrict__ label_of, int* list_b,
                                                       int* n_b) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int n_a = *P.eval_n;
-  if (r == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
+  if (r == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
   if (r >= n_a) return;
   const int g = P.eval_list[r];
   const int child = P.s_node[g];
-  int kind = reply_child(P, g, child, policy + (long long)r * CRL_N_LABELS, label_of);
+  const float* row = policy + (long long)r * CRL_N_LABELS;
+  const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
+  const int n1 = P.s_nmoves[g];
+  float best_p = -CUDART_INF_F;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < n1; i += 32) {
+    const u16 m = moves1[i];
+    const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    if (p > best_p) {
+      best_p = p;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float op = __shfl_xor_sync(0xffffffffu, best_p, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+    if (op > best_p || (op == best_p && oi < best_i)) {
+      best_p = op;
+      best_i = oi;
+    }
+  }
+  if (lane != 0) return;
+  int kind = reply_child(P, g, child, row, label_of, best_i);
   P.s_kind[g] = kind;
   if (kind == KIND_EVAL_LEAF) {
-    int row = atomicAdd(n_b, 1);
-    list_b[row] = g;
-    P.s_row[g] = row;
+    int slot = atomicAdd(n_b, 1);
+    list_b[slot] = g;
+    P.s_row[g] = slot;
   }
 }
 
-// SelfPlayTree.simulate + backprop (mctree.py:259-296) for every running game
+// SelfPlayTree.simulate + backprop (mctree.py:259-296) for every running game; one WARP per game: the lanes cache
+// the evaluated node's legal-order policy on its edge slots in parallel, lane 0 walks the backup path.
 __global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* __restrict__ policy,
                                                          const float* __restrict__ value,
                                                          const int16_t* __restrict__ label_of) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)*P.eval_n);
-  bool live = g < P.G && game_running(P, g) && P.s_kind[g] != KIND_IDLE;
-  unsigned m = __ballot_sync(0xffffffffu, live);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd((unsigned long long*)&P.counters[0], (unsigned long long)__popc(m));
-  if (!live) return;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)*P.eval_n);
+  if (g >= P.G) return;
+  if (!game_running(P, g) || P.s_kind[g] == KIND_IDLE) return;
   const int node = P.s_node[g];
   const int kind = P.s_kind[g];
+  const NodeRec& n = P.nodes[(long long)g * P.NN + node];
   double v;
   if (kind == KIND_EVAL_LEAF) {
     const int row = P.s_row[g];
-    store_priors(P, g, node, policy + (long long)row * CRL_N_LABELS, label_of);
+    const float* prow = policy + (long long)row * CRL_N_LABELS;
+    const long long ebase = (long long)g * P.EA + n.edge0;
+    const int L = n.n_legal;
+    for (int i = lane; i < L; i += 32) {     // store_priors, mirrored: legal move i -> child slot L-1-i
+      const u16 m = P.e_move[ebase + i];
+      P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    }
     v = (double)value[row];                                   // float(v) of a float32 (predict_worker.py:111)
   } else {
-    v = (double)P.nodes[(long long)g * P.NN + node].result;   // terminal: Game.get_result (mctree.py:268)
+    v = (double)n.result;                                     // terminal: Game.get_result (mctree.py:268)
   }
+  if (lane != 0) return;
+  atomicAdd((unsigned long long*)&P.counters[0], 1ull);
   backup(P, g, node, v);
 }
 
@@ -291,8 +326,8 @@ static int one_simulation(crl_engine_impl* e) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, e->d_list[1],
-                                                                     e->d_n + 1);
+    k_reply<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                                   e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);
@@ -300,7 +335,8 @@ static int one_simulation(crl_engine_impl* e) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_finalize<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value, e->d_label_of);
+    k_finalize<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
+                                                                                      e->d_label_of);
     CRL_CUDA(cudaGetLastError());
   }
   return CRL_OK;

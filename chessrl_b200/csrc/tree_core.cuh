@@ -303,10 +303,11 @@ CRL_HD int argmax_legal(const float* policy_row, const int16_t* label_of, const 
 
 // SelfPlayTree.expand, second half (mctree.py:245-249): the opponent answers with its policy argmax, the
 // child's state becomes P2, Node(new_state) lists its legal moves.
-CRL_HD int reply_child(const Pools& P, int g, int child, const float* policy_row, const int16_t* label_of) {
+CRL_HD int reply_child(const Pools& P, int g, int child, const float* policy_row, const int16_t* label_of,
+                       int pick = -1) {
   NodeRec& cn = P.nodes[(long long)g * P.NN + child];
   const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
-  int pick = argmax_legal(policy_row, label_of, moves1, P.s_nmoves[g]);
+  if (pick < 0) pick = argmax_legal(policy_row, label_of, moves1, P.s_nmoves[g]);
   u16 reply = moves1[pick];
   Board b = load_rec(cn.p1);
   make_move(b, reply);
