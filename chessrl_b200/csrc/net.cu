@@ -739,6 +739,255 @@ k_conv_v2(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUt
   }
 }
 
+// ======================================================================================================
+// v3: the whole residual tower in ONE persistent kernel.
+// A 3x3 'same' convolution of a board only reads that board, so a CTA pair can carry its boards through all 21
+// layers without any grid-wide synchronisation.  Each pair works on a GROUP of two 256-row tiles (2 x 4 boards),
+// tile X bound to tensor-memory accumulator X, and walks  for layer: for tile in (A, B): k-blocks .  While the
+// tensor cores run tile B of layer L, the epilogue warps drain tile A of layer L and publish its activations, so
+// the producer can prefetch tile A of layer L+1 as ring slots free up: no kernel boundaries, no pipeline ramp,
+// no tail wave between layers, and activations never leave L2.
+//   extra barrier: act_ready[X] (128 local epilogue arrivals) = "tile X's output of the previous layer is in global
+//   memory"; the epilogue makes its generic-proxy stores visible to the TMA (async proxy) with
+//   __threadfence + fence.proxy.async before arriving.
+// ======================================================================================================
+struct LayerDesc {
+  int map_in;            // index into the tensor-map table: 0 planes, 1 act[0], 2 act[1]
+  int map_w;             // 3 + layer
+  int k_chunks;
+  int relu;
+  int fuse_heads;
+  int write_out;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  __nv_bfloat16* out;
+};
+struct TrunkParams {
+  const int* n_dev;
+  int n_host;
+  int n_layers;
+  const float* head_w;
+  const float* head_s;
+  __nv_bfloat16* pf_out;
+  float* vf_out;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+k_trunk(const CUtensorMap* __restrict__ maps, const LayerDesc* __restrict__ layers, TrunkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + V2_STAGES * V2_A_BYTES;
+  float* s_scale = (float*)(smem + V2_STAGES * V2_STAGE_BYTES);
+  float* s_shift = s_scale + TILE_N;
+  float* s_hw = s_shift + TILE_N;
+  float* s_hs = s_hw + 3 * 256;
+  uint64_t* bars = (uint64_t*)(s_hs + 16);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + V2_STAGES;
+  uint64_t* tmem_full = bars + 2 * V2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* act_ready = tmem_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  int n_boards = p.n_host;
+  if (p.n_dev) n_boards = min(n_boards, *p.n_dev);
+  const long long total_rows = (long long)n_boards * 64;
+  const int n_tiles = (n_boards + 3) >> 2;          // 256-row tiles (4 boards)
+  const int n_groups = (n_tiles + 1) >> 1;
+  const int NL = p.n_layers;
+
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < V2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&act_ready[i], 128);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 3 * 256; i += CONV_THREADS) s_hw[i] = p.head_w[i];
+  if (threadIdx.x < 6) s_hs[threadIdx.x] = p.head_s[threadIdx.x];
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ================= TMA producer =================
+    int stage = 0;
+    uint32_t phase = 0;
+    int uses = 0;                                   // completed (tile, layer) units per accumulator slot
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const LayerDesc ld = layers[L];
+        const CUtensorMap* map_a = maps + ld.map_in;
+        const CUtensorMap* map_w = maps + ld.map_w;
+        const int n_kblocks = 9 * ld.k_chunks;
+        for (int X = 0; X < 2; ++X) {
+          const int tile = 2 * grp + X;
+          // this tile's input is the previous layer's output: wait until our own epilogue has published it
+          if (L > 0) mbar_wait(&act_ready[X], (uint32_t)((uses - 1) & 1));
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            const int tap = kb / ld.k_chunks, kc = kb - tap * ld.k_chunks;
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * V2_STAGE_BYTES);
+            tma2_load_4d(smem_a + stage * V2_A_BYTES, map_a, &full_bar[stage], kc * BLOCK_K, tap % 3 - 1, tap / 3 - 1,
+                         tile * 4 + (int)rank * 2);
+            tma2_load_2d(smem_b + stage * V2_B_BYTES, map_w, &full_bar[stage], kb * BLOCK_K, (int)rank * 128);
+            if (rank != 0) mbar_arrive_remote(&full_bar[stage], 0);
+            if (++stage == V2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (threadIdx.x == 32 && rank == 0) {
+    // ================= MMA issuer (leader CTA) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    int uses = 0;
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const int n_kblocks = 9 * layers[L].k_chunks;
+        for (int X = 0; X < 2; ++X) {
+          mbar_wait(&tmem_empty[X], (uint32_t)((uses & 1) ^ 1));
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + X * TILE_N;
+          for (int kb = 0; kb < n_kblocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint64_t da = make_kmajor_sw128_desc(smem_u32(smem_a + stage * V2_A_BYTES));
+            const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + stage * V2_B_BYTES));
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC, (kb | k) != 0);
+            umma2_commit_both(&empty_bar[stage]);
+            if (kb == n_kblocks - 1) umma2_commit_both(&tmem_full[X]);
+            if (++stage == V2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    if (uses > 0) {
+      mbar_wait(&tmem_empty[0], (uint32_t)((uses - 1) & 1));
+      mbar_wait(&tmem_empty[1], (uint32_t)((uses - 1) & 1));
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs) =================
+    const int q = warp & 3;
+    const int row_in_cta = q * 32 + lane;
+    int uses = 0;
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const LayerDesc ld = layers[L];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 128; i < TILE_N; i += 128) {
+          s_scale[i] = ld.scale[i];
+          s_shift[i] = ld.shift[i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int X = 0; X < 2; ++X) {
+          const int tile = 2 * grp + X;
+          mbar_wait(&tmem_full[X], (uint32_t)(uses & 1));
+          tcgen05_fence_after();
+          const long long grow = (long long)tile * 256 + rank * 128 + row_in_cta;
+          const bool valid = grow < total_rows;
+          __nv_bfloat16* orow = ld.write_out ? ld.out + grow * TILE_N : nullptr;
+          const __nv_bfloat16* rrow = ld.residual ? ld.residual + grow * TILE_N : nullptr;
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + X * TILE_N + c0, v);
+            tmem_ld_wait();
+            if (!valid) continue;
+            uint4 res[4];
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + c0 + 8 * j);
+            }
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t* rj = reinterpret_cast<const uint32_t*>(&res[j]);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  a[8 * j + 2 * h] += __uint_as_float(rj[h] << 16);
+                  a[8 * j + 2 * h + 1] += __uint_as_float(rj[h] & 0xFFFF0000u);
+                }
+              }
+            }
+            if (ld.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+            }
+            if (ld.fuse_heads) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = __bfloat162float(__float2bfloat16_rn(a[j]));
+                h0 = fmaf(x, s_hw[c0 + j], h0);
+                h1 = fmaf(x, s_hw[256 + c0 + j], h1);
+                h2 = fmaf(x, s_hw[512 + c0 + j], h2);
+              }
+            }
+            if (orow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(a[8 * j + 2 * h], a[8 * j + 2 * h + 1]);
+                  pk[h] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive_remote(&tmem_empty[X], 0);
+          if (ld.fuse_heads && valid) {
+            const float f0 = fmaxf(h0 * s_hs[0] + s_hs[3], 0.f), f1 = fmaxf(h1 * s_hs[1] + s_hs[4], 0.f);
+            reinterpret_cast<__nv_bfloat162*>(p.pf_out)[grow] = __floats2bfloat162_rn(f0, f1);
+            p.vf_out[grow] = fmaxf(h2 * s_hs[2] + s_hs[5], 0.f);
+          }
+          // publish this tile's activations to the TMA unit (generic proxy -> async proxy), then release the producer
+          __threadfence();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          mbar_arrive(&act_ready[X]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // softmax over the policy logits + the value head's two dense layers; 8 positions per block, one warp each
 struct TailParams {
   const int* n_rows_dev;
@@ -853,6 +1102,12 @@ struct NetWeights {
   float* bp_pad = nullptr;                  // [2048]
   float* ones = nullptr;                    // [2048]
   CUtensorMap map_pf, map_wp;
+  // v3 (whole tower in one persistent kernel)
+  bool use_trunk = true;
+  CUtensorMap* d_maps = nullptr;            // [3 + N_CONVS] device copies: planes, act[0], act[1], weights (128-filter boxes)
+  LayerDesc* d_layers = nullptr;            // [N_CONVS]
+  const void* d_planes_map_for = nullptr;   // planes pointer / rows the device copy of map 0 was built for
+  int d_planes_map_rows = 0;
 };
 
 static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int cin, int rows) {
@@ -950,6 +1205,48 @@ int net_create(crl_engine_impl* e) {
   CRL_CUDA(cudaFuncSetAttribute(k_conv3x3, cudaFuncAttributeMaxDynamicSharedMemorySize, CONV_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_conv_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
+  {
+    // tensor-map table + layer table for the whole-tower kernel
+    const char* nt = getenv("CRL_NO_TRUNK");
+    nw->use_trunk = nw->use_v2 && !(nt && nt[0] == '1');
+    if ((rc = dev_alloc(e, &nw->d_maps, 3 + N_CONVS))) return rc;
+    if ((rc = dev_alloc(e, &nw->d_layers, N_CONVS))) return rc;
+    std::vector<CUtensorMap> hm(3 + N_CONVS);
+    memset(hm.data(), 0, hm.size() * sizeof(CUtensorMap));
+    hm[1] = nw->map_act[0];
+    hm[2] = nw->map_act[1];
+    for (int i = 0; i < N_CONVS; ++i) hm[3 + i] = nw->map_w2[i];
+    CRL_CUDA(cudaMemcpyAsync(nw->d_maps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
+    std::vector<LayerDesc> hl(N_CONVS);
+    for (int L = 0; L < N_CONVS; ++L) {
+      LayerDesc& d = hl[L];
+      memset(&d, 0, sizeof(d));
+      d.map_w = 3 + L;
+      d.k_chunks = nw->cin[L] / BLOCK_K;
+      d.scale = nw->scale[L];
+      d.shift = nw->shift[L];
+      if (L == 0) {                      // stem: planes -> act[0], no BN / activation
+        d.map_in = 0;
+        d.out = nw->act[0];
+        d.write_out = 1;
+      } else if ((L - 1) % 2 == 0) {     // conv_a: act[0] -> act[1], BN + ReLU
+        d.map_in = 1;
+        d.out = nw->act[1];
+        d.relu = 1;
+        d.write_out = 1;
+      } else {                           // conv_b: act[1] -> act[0] in place (+ residual act[0]), BN, ReLU
+        d.map_in = 2;
+        d.out = nw->act[0];
+        d.residual = nw->act[0];
+        d.relu = 1;
+        d.write_out = L != N_CONVS - 1;  // the last layer only feeds the fused heads
+        d.fuse_heads = L == N_CONVS - 1;
+      }
+    }
+    CRL_CUDA(cudaMemcpyAsync(nw->d_layers, hl.data(), hl.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaStreamSynchronize(e->stream));
+  }
   return CRL_OK;
 }
 
@@ -1185,6 +1482,32 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     }
   }
   int rc;
+  if (nw->use_trunk) {
+    if (nw->d_planes_map_for != nw->planes_ptr || nw->d_planes_map_rows != nw->planes_rows) {
+      // stream-ordered update of map 0 (planes); the copy source must outlive the async copy -> keep it in NetWeights
+      CRL_CUDA(cudaMemcpyAsync(nw->d_maps, &nw->map_planes, sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
+      CRL_CUDA(cudaStreamSynchronize(e->stream));
+      nw->d_planes_map_for = nw->planes_ptr;
+      nw->d_planes_map_rows = nw->planes_rows;
+    }
+    TrunkParams tp;
+    tp.n_dev = n_dev;
+    tp.n_host = n_host;
+    tp.n_layers = N_CONVS;
+    tp.head_w = nw->w1x1;
+    tp.head_s = nw->s1x1;
+    tp.pf_out = nw->pf;
+    tp.vf_out = nw->vf;
+    int groups = ((n_host + 3) / 4 + 1) / 2;
+    int pairs = groups < nw->n_sms / 2 ? groups : nw->n_sms / 2;
+    if (pairs < 1) pairs = 1;
+    {
+      LaunchScope ls(e, KC_CONV);
+      k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->d_maps, nw->d_layers, tp);
+      CRL_CUDA(cudaGetLastError());
+    }
+    return launch_heads_v2(e, n_dev, n_host, policy, value);
+  }
   if (nw->use_v2) {
     if ((rc = launch_conv_v2(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0, false))) return rc;
     for (int b = 0; b < 10; ++b) {
