@@ -41,7 +41,7 @@ struct NodeRec {
   int8_t result;  // Game.get_result of p2, RESULT_NONE while running
   u8 slot;        // index among the parent's children (creation order)
   u8 has_p1;      // 0 for the root
-  u8 pad;
+  u8 pending;     // wave mode: created in the current wave, its reply (network evaluation of p1) is not known yet
 };
 
 struct Pools {
@@ -64,15 +64,19 @@ struct Pools {
   double* e_value;
   int* e_child;
   int8_t* e_result;
+  u8* e_vloss;      // [G][EA] Node.vloss of the child on this edge (mctree.py:36, 226-227, 292-293); 0 outside a wave
   int* r_visits;    // [G]
   double* r_value;  // [G]
-  // --- per-simulation scratch ---
-  int* s_node;      // [G] selected node / new child
-  int* s_kind;      // [G]
-  u16* s_moves;     // [G][MAX_MOVES] legal moves of the position awaiting its reply
-  int* s_nmoves;    // [G]
-  int* s_row;       // [G] row of this game in the current evaluation batch
-  int* eval_list;   // [G] game of every batch row
+  // --- per-simulation scratch: one SLOT per in-flight simulation, slot = g*K + j (K = 1: slot = game) ---
+  int K;            // in-flight simulations per game of the kernels being launched (1 = the exact threads=1 schedule)
+  int* s_node;      // [G*K] selected node / new child
+  int* s_kind;      // [G*K]
+  u16* s_moves;     // [G*K][MAX_MOVES] legal moves of the position awaiting its reply
+  int* s_nmoves;    // [G*K]
+  int* s_row;       // [G*K] row of this slot in the current evaluation batch
+  int* s_wave_n;    // [G] slots used by the current wave
+  int* g_sims_left; // [G] simulations of the current crl_mcts_simulate call still to run (wave mode)
+  int* eval_list;   // [G*K] slot of every batch row
   int* eval_n;      // [1]
   int* err;         // [1] ERR_* flags
   long long* counters;  // [0] simulations [1] evaluations
@@ -165,30 +169,32 @@ CRL_HD int count_repetitions(const Pools& P, int g, Cursor c, u64 key, int revle
 // ---------------------------------------------------------------------------------------------------
 // PUCT score of one edge: Node.get_value (mctree.py:71-87), float64 with the one float32 product
 // ---------------------------------------------------------------------------------------------------
-CRL_HD double edge_score(int visits, double value, float prior, int child_result) {
+CRL_HD double edge_score(int visits, double value, float prior, int child_result, int vloss = 0) {
   double n1 = (double)(1 + visits);
   int sub = (child_result != RESULT_NONE || visits < 2) ? 0 : visits - 1;
   float cp = 10.0f * prior;                      // int * np.float32 -> float32
 #if defined(__CUDA_ARCH__)
   double q = __ddiv_rn(value, n1);
   double u = __dmul_rn((double)cp, __ddiv_rn(__dsqrt_rn((double)sub), n1));
-  return __dadd_rn(q, u);
+  return __dsub_rn(__dadd_rn(q, u), (double)vloss);   // "return value - self.vloss" (mctree.py:87)
 #else
   volatile double q = value / n1;
   volatile double s = __builtin_sqrt((double)sub);
   volatile double r = s / n1;
   volatile double u = (double)cp * r;
-  return q + u;
+  volatile double qu = q + u;
+  return qu - (double)vloss;
 #endif
 }
 
 // serial child scan (first maximum).  The device kernel uses a warp-cooperative version of this loop.
-CRL_HD int best_edge_serial(const Pools& P, int g, const NodeRec& n) {
+CRL_HD int best_edge_serial(const Pools& P, int g, const NodeRec& n, bool with_vloss = false) {
   long long base = (long long)g * P.EA + n.edge0;
   int best = 0;
   double best_s = 0;
   for (int k = 0; k < n.n_exp; ++k) {
-    double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k]);
+    double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k],
+                          with_vloss ? (int)P.e_vloss[base + k] : 0);
     if (k == 0 || s > best_s) {
       best_s = s;
       best = k;
@@ -219,6 +225,35 @@ CRL_HD void select_descend(const Pools& P, int g, Scan scan, int* out_node, int*
   }
 }
 
+// Wave mode (K > 1 in-flight simulations per game = one legal schedule of the reference's threads=K pool: the K
+// selects run one after the other, then the K simulates, then the K backprops in the same order).  A select of the
+// wave may not enter a node created earlier in the SAME wave whose opponent reply is still unknown (it needs the
+// network evaluation of this wave): the wave is cut there and the simulation runs in the next wave -- which is the
+// schedule "fewer than K workers were active", equally legal for the reference.
+// returns 0 = expand *out_node, 1 = *out_node is a terminal leaf, 2 = cut (pending node reached)
+template <class Scan>
+CRL_HD int select_descend_wave(const Pools& P, int g, Scan scan, int* out_node) {
+  int node = 0;
+  for (;;) {
+    const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+    if (n.pending) return 2;
+    *out_node = node;
+    if (n.result != RESULT_NONE) return 1;
+    if (n.n_exp < n.n_legal) return 0;
+    int k = scan(n);
+    node = P.e_child[(long long)g * P.EA + n.edge0 + k];
+  }
+}
+
+// leaf.vloss += d (mctree.py:226-227 / 292-293); the root's vloss is never read (its score is never compared)
+CRL_HD void vloss_add(const Pools& P, int g, int node, int d) {
+  if (node <= 0) return;
+  const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+  const NodeRec& pn = P.nodes[(long long)g * P.NN + n.parent];
+  long long e = (long long)g * P.EA + pn.edge0 + n.slot;
+  P.e_vloss[e] = (u8)((int)P.e_vloss[e] + d);
+}
+
 // generate the legal moves of `b`, its transposition key and Game.get_result, given where it sits
 CRL_HD int analyse_position(const Pools& P, int g, const Board& b, Cursor at, u16* moves, int* n_moves, u64* key) {
   StoreSink sink{moves, 0};
@@ -234,7 +269,7 @@ CRL_HD int analyse_position(const Pools& P, int g, const Board& b, Cursor at, u1
 
 // SelfPlayTree.expand, first half (mctree.py:241-244): pop the last unexpanded action of `parent`, play it,
 // create the child.  Returns the kind of follow-up the child needs.
-CRL_HD int expand_child(const Pools& P, int g, int parent, int* out_child) {
+CRL_HD int expand_child(const Pools& P, int g, int slot, int parent, int* out_child) {
   NodeRec& pn = P.nodes[(long long)g * P.NN + parent];
   int child = P.g_nnodes[g];
   if (child >= P.NN) {
@@ -258,20 +293,22 @@ CRL_HD int expand_child(const Pools& P, int g, int parent, int* out_child) {
   cn.n_exp = 0;
   cn.n_legal = 0;
   cn.edge0 = 0;
+  cn.pending = 0;
   P.e_child[ebase + k] = child;
   P.e_visits[ebase + k] = 0;
   P.e_value[ebase + k] = 0.0;
+  P.e_vloss[ebase + k] = 0;
   // e_prior[k] already holds this child's prior: store_priors() wrote the parent's legal-order policy
   // mirrored (legal move j -> slot n_legal-1-j), which is zip(priors, reversed(children)) (mctree.py:298-303).
   pn.n_exp = (u16)(k + 1);
 
   Cursor at{child, 1, meta_ply(b.meta)};
-  u16* moves = P.s_moves + (long long)g * MAX_MOVES;
+  u16* moves = P.s_moves + (long long)slot * MAX_MOVES;
   int n_moves;
   u64 key;
   int res = analyse_position(P, g, b, at, moves, &n_moves, &key);
   cn.key1 = key;
-  P.s_nmoves[g] = n_moves;
+  P.s_nmoves[slot] = n_moves;
   *out_child = child;
   if (res != RESULT_NONE) {        // the game ended on our move: the child's state is P1 (mctree.py:244)
     store_rec(cn.p2, b);
@@ -282,6 +319,7 @@ CRL_HD int expand_child(const Pools& P, int g, int parent, int* out_child) {
     return KIND_NEW_TERMINAL;
   }
   cn.result = RESULT_NONE;
+  cn.pending = 1;                  // until reply_child; only wave-mode selects can meet it
   P.e_result[ebase + k] = RESULT_NONE;
   return KIND_NEED_REPLY;
 }
@@ -303,11 +341,11 @@ CRL_HD int argmax_legal(const float* policy_row, const int16_t* label_of, const 
 
 // SelfPlayTree.expand, second half (mctree.py:245-249): the opponent answers with its policy argmax, the
 // child's state becomes P2, Node(new_state) lists its legal moves.
-CRL_HD int reply_child(const Pools& P, int g, int child, const float* policy_row, const int16_t* label_of,
+CRL_HD int reply_child(const Pools& P, int g, int slot, int child, const float* policy_row, const int16_t* label_of,
                        int pick = -1) {
   NodeRec& cn = P.nodes[(long long)g * P.NN + child];
-  const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
-  if (pick < 0) pick = argmax_legal(policy_row, label_of, moves1, P.s_nmoves[g]);
+  const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
+  if (pick < 0) pick = argmax_legal(policy_row, label_of, moves1, P.s_nmoves[slot]);
   u16 reply = moves1[pick];
   Board b = load_rec(cn.p1);
   make_move(b, reply);
@@ -322,17 +360,26 @@ CRL_HD int reply_child(const Pools& P, int g, int child, const float* policy_row
   cn.key2 = key;
   cn.result = (int8_t)res;
   cn.n_legal = (u16)n2;
+  cn.pending = 0;
   const NodeRec& pn = P.nodes[(long long)g * P.NN + cn.parent];
   P.e_result[(long long)g * P.EA + pn.edge0 + cn.slot] = (int8_t)res;
   if (res != RESULT_NONE) return KIND_NEW_TERMINAL;
-  // reserve the node's edge slots and remember its legal moves (Node.unexpanded_actions, mctree.py:31)
+  // reserve the node's edge slots and remember its legal moves (Node.unexpanded_actions, mctree.py:31).
+  // In wave mode several rows of one game run concurrently, hence the atomic; where a node's edges sit inside
+  // the game's arena has no influence on any result.
+#if defined(__CUDA_ARCH__)
+  int e0 = atomicAdd(&P.g_nedges[g], n2);
+#else
   int e0 = P.g_nedges[g];
+  P.g_nedges[g] = e0 + n2;
+#endif
   if (e0 + n2 > P.EA) {
     *P.err |= ERR_EDGE_OVERFLOW;
+    cn.n_legal = 0;
     cn.result = 0;   // poison as a drawn leaf so the search stays well-defined; the host raises on err
+    P.e_result[(long long)g * P.EA + pn.edge0 + cn.slot] = 0;
     return KIND_NEW_TERMINAL;
   }
-  P.g_nedges[g] = e0 + n2;
   cn.edge0 = e0;
   long long ebase = (long long)g * P.EA + e0;
   for (int i = 0; i < n2; ++i) P.e_move[ebase + i] = moves2[i];
@@ -426,6 +473,7 @@ CRL_HD int root_init(const Pools& P, int g) {
   r.reply = MOVE_NONE;
   r.n_exp = 0;
   r.edge0 = 0;
+  r.pending = 0;
   int ply = meta_ply(b.meta);
   r.key2 = r.key1 = P.g_keys[(long long)(ply % KEY_RING) * P.G + g];
   r.result = P.g_result[g];
