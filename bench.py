@@ -235,6 +235,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--games", type=int, default=4096, help="lockstep games per GPU")
     ap.add_argument("--sims", type=int, default=200, help="simulations per move")
+    ap.add_argument("--inflight", type=int, default=1, help="simulations in flight per game (reference --threads); 1 = exact schedule")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-perft", action="store_true")
@@ -262,7 +263,8 @@ def main():
     peaks = load_peaks()
     G, S = args.games, args.sims
 
-    eng = Engine(max_games=G, max_nodes=S + 1, avg_moves=64)
+    K = max(1, args.inflight)
+    eng = Engine(max_games=G, max_nodes=S + 1, avg_moves=64, max_inflight=K)
     pack = model.random_pack(seed=0)
     if world > 1:
         # weights live on rank 0 and are broadcast over NCCL (the only collective on this path besides timing)
@@ -277,7 +279,8 @@ def main():
     eng.load_weights(pack)
     eng.set_evaluator(EVAL_NET)
     start, move_lists = synthetic_games(eng, G, seed=1234 + rank)
-    eng.games_set(start, move_lists)
+    packed = eng.pack_move_lists(move_lists)                                # host buffers (uint16 moves, int32 counts)
+    eng.games_set(start, packed)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
     def barrier():
@@ -287,12 +290,12 @@ def main():
 
     def device_step():
         eng.mcts_begin_move()
-        eng.mcts_simulate(S)
+        eng.mcts_simulate(S, K)
 
     def e2e_step():
-        eng.games_set(start, move_lists)                                   # host -> device (records + move lists)
+        eng.games_set(start, packed)                                       # host -> device (records + move lists)
         eng.mcts_begin_move()
-        eng.mcts_simulate(S)
+        eng.mcts_simulate(S, K)
         st = eng.root_stats(want=("visits",))                              # device -> host
         _, plies, results = eng.games_get(0, G)
         picks = np.full(G, -1, dtype=np.int32)
@@ -352,7 +355,7 @@ def main():
         eng.profile(True)
         c0 = eng.counters()
         eng.mcts_begin_move()
-        eng.mcts_simulate(min(S, 16))
+        eng.mcts_simulate(min(S, 16 * K), K)
         torch.cuda.synchronize()
         prof = eng.profile_read()
         c1 = eng.counters()
@@ -387,14 +390,15 @@ def main():
                          "evaluations in %.1f s; oracle port (python-chess restatement + mctree restatement + torch-CPU fp32 net)" % (s, ev, t)}
 
     if rank == 0:
-        bytes_h2d = G * 72 + G * 4 + sum(len(m) for m in move_lists) * 2 + G * 4
+        bytes_h2d = G * 72 + G * 4 + int(packed[0].nbytes) + G * 4     # records, counts, padded move lists, picks
         bytes_d2h = G * 256 * 4 + 3 * G * 4 + G * 8 + G * 72 + G * 5 + G * 4
         line = {
             "metric": "mcts_simulations_per_sec", "value": value, "unit": "simulations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD(args), "games_per_gpu": G, "sims_per_move": S,
-                       "step": "one move search for all lanes = G*S simulations", "schedule": "1 in-flight simulation per game (exact threads=1 parity mode)",
+                       "step": "one move search for all lanes = G*S simulations", "schedule": ("1 in-flight simulation per game (exact threads=1 parity mode)" if K == 1 else
+                                    "waves of up to %d in-flight simulations per game (reference --threads %d)" % (K, K)),
                        "l2": "256 MiB buffer written between timed steps; working set (trees + activations) > L2",
                        "parallelism": "games sharded by lane across %d GPU(s), no per-simulation collective" % world},
             "clocks": clocks,

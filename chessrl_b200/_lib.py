@@ -38,6 +38,8 @@ class NodeHost(ctypes.Structure):
 # name -> (restype, argtypes); every symbol include/chessrl_b200.h declares
 SIGNATURES = {
     "crl_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
+    "crl_create_ex": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, vp]),
     "crl_destroy": (ctypes.c_int, [vp]),
     "crl_last_error": (ctypes.c_char_p, []),
     "crl_version": (ctypes.c_int, []),

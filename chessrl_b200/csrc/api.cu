@@ -195,8 +195,14 @@ const char* crl_last_error(void) { return g_err; }
 int crl_version(void) { return 100; }
 
 int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, void* stream) {
-  if (!out || max_games <= 0 || max_nodes <= 0) {
-    set_error("crl_create: bad arguments");
+  return crl_create_ex(out, device, max_games, max_nodes, avg_moves, 1, stream);
+}
+
+int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, int max_inflight,
+                  void* stream) {
+  if (!out || max_games <= 0 || max_nodes <= 0 || max_inflight < 1 || max_inflight > CRL_MAX_INFLIGHT ||
+      (long long)max_games * max_inflight > (1ll << 24)) {
+    set_error("crl_create: bad arguments (max_games %d, max_nodes %d, max_inflight %d)", max_games, max_nodes, max_inflight);
     return CRL_EINVAL;
   }
   int n_dev = 0;
@@ -231,6 +237,9 @@ int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int a
     e->use_graph = !(g && g[0] == '1');
   }
   e->G = max_games;
+  e->Kmax = max_inflight;
+  e->R = max_games * max_inflight;
+  e->cur_rows = max_games;
   e->NN = max_nodes + 1;
   if (avg_moves <= 0) avg_moves = 64;
   long long ea = (long long)e->NN * avg_moves;
@@ -240,7 +249,8 @@ int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int a
   P.G = e->G;
   P.NN = e->NN;
   P.EA = e->EA;
-  const size_t G = e->G;
+  P.K = 1;
+  const size_t G = e->G, R = e->R;
   int rc = CRL_OK;
 #define A(field, count) if (rc == CRL_OK) rc = pool_alloc(e, &P.field, (size_t)(count))
   A(g_cur, 9 * G);
@@ -259,24 +269,27 @@ int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int a
   A(e_value, G * e->EA);
   A(e_child, G * e->EA);
   A(e_result, G * e->EA);
+  A(e_vloss, G * e->EA);
   A(r_visits, G);
   A(r_value, G);
-  A(s_node, G);
-  A(s_kind, G);
-  A(s_moves, G * MAX_MOVES);
-  A(s_nmoves, G);
-  A(s_row, G);
+  A(s_node, R);
+  A(s_kind, R);
+  A(s_moves, R * MAX_MOVES);
+  A(s_nmoves, R);
+  A(s_row, R);
+  A(s_wave_n, G);
+  A(g_sims_left, G);
   A(err, 1);
   A(counters, 4);
 #undef A
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_list[0], G);
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_list[1], G);
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_n, 2);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_list[0], R);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_list[1], R);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_n, 4);
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_tmp_moves, 2 * G);
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_tmp_pick, G);
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_planes, (G + 2) * 64 * 128);
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_policy, (G + 2) * CRL_N_LABELS);
-  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_value, G + 2);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_planes, (R + 2) * 64 * 128);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_policy, (R + 2) * CRL_N_LABELS);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_value, R + 2);
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_label_of, 5 * 4096);
   if (rc == CRL_OK) {
     P.eval_list = e->d_list[0];
@@ -575,15 +588,16 @@ int crl_mcts_simulate(crl_engine* e, int n_sims, int inflight) {
     set_error("crl_mcts_simulate: call crl_mcts_begin_move first");
     return CRL_ESTATE;
   }
-  if (inflight != 1) {
-    set_error("crl_mcts_simulate: only inflight = 1 (the deterministic threads=1 schedule) is implemented");
+  if (inflight < 1 || inflight > e->Kmax) {
+    set_error("crl_mcts_simulate: inflight = %d, but the engine was created for at most %d in-flight simulations "
+              "per game (crl_create_ex max_inflight)", inflight, e->Kmax);
     return CRL_EINVAL;
   }
   if (n_sims < 0 || n_sims > e->NN - 1) {
     set_error("crl_mcts_simulate: %d simulations exceed the node pool (%d per game)", n_sims, e->NN - 1);
     return CRL_EINVAL;
   }
-  return tree_simulate(e, n_sims);
+  return tree_simulate(e, n_sims, inflight);
 }
 
 int crl_mcts_root_stats_host(crl_engine* e, int32_t* child_visits, double* child_values, float* child_priors,

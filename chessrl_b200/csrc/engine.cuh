@@ -29,6 +29,9 @@ struct crl_engine_impl {
   int device = 0;
   cudaStream_t stream = nullptr;
   int G = 0, NN = 0, EA = 0;
+  int Kmax = 1;                    // in-flight simulations per game the workspaces are sized for
+  int R = 0;                       // evaluation row capacity = G * Kmax
+  int cur_rows = 0;                // host bound on the rows of the batch being launched (G, or G*K in wave mode)
   Pools P{};                       // device pointers
   std::vector<void*> allocs;       // everything cudaMalloc'ed
   int16_t* d_label_of = nullptr;   // [5][64][64]
@@ -119,7 +122,8 @@ int launch_game_info(crl_engine_impl* e, int first, int n, u16* legal, int* n_le
 int launch_game_moves(crl_engine_impl* e, const u16* moves_per_game /*[G]*/, u8* accepted /*[G] or null*/);
 int launch_eval_batch(crl_engine_impl* e, int which_mode);   // encodes eval_list rows and runs the evaluator
 int tree_begin_move(crl_engine_impl* e, const u8* mask_dev);
-int tree_simulate(crl_engine_impl* e, int n_sims);
+int tree_simulate(crl_engine_impl* e, int n_sims, int K);
+int tree_run_steps(crl_engine_impl* e, int n_steps, int K);
 int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev);
 int tree_commit(crl_engine_impl* e, const int* pick_dev, u16* out_moves_dev, int apply);
 

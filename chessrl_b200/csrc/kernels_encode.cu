@@ -94,16 +94,18 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_boards(const u64* __rest
   write_planes(s, s_mask, planes + (long long)i * 64 * 128);
 }
 
-// tree / game batches: row r -> game eval_list[r]; position = (s_node[g], which) or the root when which==0
+// tree / game batches: row r -> slot eval_list[r] (game = slot / K); position = (s_node[slot], which) or the root
+// when which==0
 __global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
                                                              __nv_bfloat16* __restrict__ planes) {
   __shared__ EncShared s;
   __shared__ unsigned s_mask[64][4];
   const int r = blockIdx.x;
   if (r >= *P.eval_n) return;
-  const int g = P.eval_list[r];
+  const int slot = P.eval_list[r];
+  const int g = slot / P.K;
   if (threadIdx.x == 0) {
-    const int node = which == 0 ? 0 : P.s_node[g];
+    const int node = which == 0 ? 0 : P.s_node[slot];
     const int w = which == 0 ? 2 : which;
     const NodeRec& nr = P.nodes[(long long)g * P.NN + node];
     const u64 meta = (w == 2 ? nr.p2 : nr.p1)[8];
@@ -154,8 +156,9 @@ __global__ void __launch_bounds__(256) k_hash_eval_rows(Pools P, int which, u64 
                                                         float* __restrict__ policy, float* __restrict__ value) {
   const int r = blockIdx.x;
   if (r >= *P.eval_n) return;
-  const int g = P.eval_list[r];
-  const int node = which == 0 ? 0 : P.s_node[g];
+  const int slot = P.eval_list[r];
+  const int g = slot / P.K;
+  const int node = which == 0 ? 0 : P.s_node[slot];
   const NodeRec& nr = P.nodes[(long long)g * P.NN + node];
   Board b = load_rec((which == 1) ? nr.p1 : nr.p2);
   hash_eval_row(b, seed, bits, policy + (long long)r * CRL_N_LABELS, value + r);
@@ -190,16 +193,16 @@ int launch_hash_eval_boards(crl_engine_impl* e, const u64* boards, int n, u64 se
 int launch_eval_batch(crl_engine_impl* e, int which) {
   if (e->eval_kind == CRL_EVAL_HASH) {
     LaunchScope ls(e, KC_HASHEVAL);
-    k_hash_eval_rows<<<e->G, 256, 0, e->stream>>>(e->P, which, e->eval_seed, e->eval_bits, e->d_policy, e->d_value);
+    k_hash_eval_rows<<<e->cur_rows, 256, 0, e->stream>>>(e->P, which, e->eval_seed, e->eval_bits, e->d_policy, e->d_value);
     CRL_CUDA(cudaGetLastError());
     return CRL_OK;
   }
   {
     LaunchScope ls(e, KC_ENCODE);
-    k_encode_rows<<<e->G, ENC_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
+    k_encode_rows<<<e->cur_rows, ENC_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
     CRL_CUDA(cudaGetLastError());
   }
-  return net_forward(e, e->d_planes, e->G, e->P.eval_n, e->d_policy, e->d_value);
+  return net_forward(e, e->d_planes, e->cur_rows, e->P.eval_n, e->d_policy, e->d_value);
 }
 
 }  // namespace crl

@@ -23,6 +23,8 @@ __device__ __forceinline__ bool game_running(const Pools& P, int g) {
   return P.g_active[g] && P.g_result[g] == RESULT_NONE;
 }
 
+// VL: subtract the children's virtual loss (wave mode; with one in-flight simulation it is always zero)
+template <bool VL>
 struct WarpScan {
   const Pools& P;
   int g, lane;
@@ -32,7 +34,8 @@ struct WarpScan {
     double best_s = -CUDART_INF;
     int best_k = 0x7fffffff;
     for (int k = lane; k < cnt; k += 32) {
-      double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k]);
+      double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k],
+                            VL ? (int)P.e_vloss[base + k] : 0);
       if (s > best_s) {
         best_s = s;
         best_k = k;
@@ -60,7 +63,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
     return;
   }
   int node, term;
-  select_descend(P, g, WarpScan{P, g, lane}, &node, &term);
+  select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
   if (lane != 0) return;
   if (term) {
     P.s_node[g] = node;
@@ -68,7 +71,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
     return;
   }
   int child;
-  int kind = expand_child(P, g, node, &child);
+  int kind = expand_child(P, g, g, node, &child);
   P.s_node[g] = child;
   P.s_kind[g] = kind;
   if (kind == KIND_NEED_REPLY) {
@@ -76,6 +79,93 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
     P.eval_list[row] = g;
     P.s_row[g] = row;
   }
+}
+
+// ---- wave mode: K in-flight simulations per game (the reference's --threads K, mctree.py:173-176) -----------
+// One WARP per game runs the wave's selects one after the other (each sees the virtual losses and the
+// expansions of the earlier ones, exactly as in the schedule described at select_descend_wave); slot j of
+// game g is scratch index g*K + j.  The wave ends early when a select would enter a node whose reply is still
+// being evaluated.
+__global__ void __launch_bounds__(TREE_BLOCK) k_wave_begin(Pools P, int n_sims) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= P.G) return;
+  P.g_sims_left[g] = game_running(P, g) ? n_sims : 0;
+  P.s_wave_n[g] = 0;
+}
+
+__global__ void __launch_bounds__(TREE_BLOCK) k_select_wave(Pools P) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= P.G) return;
+  const int left = game_running(P, g) ? P.g_sims_left[g] : 0;
+  const int kmax = min(P.K, left);
+  int used = 0;
+  for (int j = 0; j < kmax; ++j) {
+    int node = 0;
+    const int what = select_descend_wave(P, g, WarpScan<true>{P, g, lane}, &node);
+    if (what == 2) break;
+    if (lane == 0) {
+      const int slot = g * P.K + used;
+      if (wave_take_slot(P, g, slot, what, node) == KIND_NEED_REPLY) {
+        const int row = atomicAdd(P.eval_n, 1);
+        P.eval_list[row] = slot;
+        P.s_row[slot] = row;
+      }
+      __threadfence_block();
+    }
+    __syncwarp();
+    ++used;
+  }
+  if (lane == 0) {
+    P.s_wave_n[g] = used;
+    P.g_sims_left[g] = left - used;
+  }
+}
+
+// simulate + backprop of the wave, in slot order (value += v is a float64 sum: the order is part of the result)
+__global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const float* __restrict__ policy,
+                                                              const float* __restrict__ value,
+                                                              const int16_t* __restrict__ label_of) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)*P.eval_n);
+  if (g >= P.G) return;
+  const int used = P.s_wave_n[g];
+  for (int j = 0; j < used; ++j) {
+    const int slot = g * P.K + j;
+    const int node = P.s_node[slot];
+    const int kind = P.s_kind[slot];
+    if (kind == KIND_IDLE) continue;          // node pool overflow (flagged in P.err)
+    const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+    double v;
+    if (kind == KIND_EVAL_LEAF) {
+      const int row = P.s_row[slot];
+      const float* prow = policy + (long long)row * CRL_N_LABELS;
+      const long long ebase = (long long)g * P.EA + n.edge0;
+      const int L = n.n_legal;
+      for (int i = lane; i < L; i += 32) {
+        const u16 m = P.e_move[ebase + i];
+        P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+      }
+      v = (double)value[row];
+    } else {
+      v = (double)n.result;
+    }
+    if (lane == 0) {
+      backup(P, g, node, v);
+      vloss_add(P, g, node, -1);
+    }
+  }
+  if (lane == 0 && used > 0) atomicAdd((unsigned long long*)&P.counters[0], (unsigned long long)used);
+}
+
+// largest number of simulations any game still has to run (the host loops on it)
+__global__ void __launch_bounds__(256) k_wave_left(Pools P, int* out) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  int v = (g < P.G && game_running(P, g)) ? P.g_sims_left[g] : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, off));
+  if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
 // rows of batch A (positions after our move) -> opponent reply, node state, batch B.
@@ -89,11 +179,12 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __re
   const int n_a = *P.eval_n;
   if (r == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
   if (r >= n_a) return;
-  const int g = P.eval_list[r];
-  const int child = P.s_node[g];
+  const int slot = P.eval_list[r];
+  const int g = slot / P.K;
+  const int child = P.s_node[slot];
   const float* row = policy + (long long)r * CRL_N_LABELS;
-  const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
-  const int n1 = P.s_nmoves[g];
+  const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
+  const int n1 = P.s_nmoves[slot];
   float best_p = -CUDART_INF_F;
   int best_i = 0x7fffffff;
   for (int i = lane; i < n1; i += 32) {
@@ -114,12 +205,12 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __re
     }
   }
   if (lane != 0) return;
-  int kind = reply_child(P, g, child, row, label_of, best_i);
-  P.s_kind[g] = kind;
+  int kind = reply_child(P, g, slot, child, row, label_of, best_i);
+  P.s_kind[slot] = kind;
   if (kind == KIND_EVAL_LEAF) {
-    int slot = atomicAdd(n_b, 1);
-    list_b[slot] = g;
-    P.s_row[g] = slot;
+    int rb = atomicAdd(n_b, 1);
+    list_b[rb] = slot;
+    P.s_row[slot] = rb;
   }
 }
 
@@ -298,6 +389,8 @@ static int use_list(crl_engine_impl* e, int which) {
 int tree_begin_move(crl_engine_impl* e, const u8* mask_dev) {
   CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
   use_list(e, 0);
+  e->P.K = 1;                 // root batch: one row per game
+  e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
     k_root_init<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mask_dev);
@@ -317,6 +410,8 @@ int tree_begin_move(crl_engine_impl* e, const u8* mask_dev) {
 static int one_simulation(crl_engine_impl* e) {
   CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
   use_list(e, 0);
+  e->P.K = 1;
+  e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
     k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
@@ -342,27 +437,98 @@ static int one_simulation(crl_engine_impl* e) {
   return CRL_OK;
 }
 
+// one WAVE of every running game: up to K selects per game, two evaluation batches of up to G*K rows, backups
+static int one_wave(crl_engine_impl* e, int K) {
+  CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
+  use_list(e, 0);
+  e->P.K = K;
+  e->cur_rows = e->G * K;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_select_wave<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
+    CRL_CUDA(cudaGetLastError());
+  }
+  int rc = launch_eval_batch(e, 1);
+  if (rc != CRL_OK) return rc;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_reply<<<div_up((long long)e->cur_rows * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                                         e->d_list[1], e->d_n + 1);
+    CRL_CUDA(cudaGetLastError());
+  }
+  use_list(e, 1);
+  rc = launch_eval_batch(e, 2);
+  if (rc != CRL_OK) return rc;
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_finalize_wave<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
+                                                                                           e->d_label_of);
+    CRL_CUDA(cudaGetLastError());
+  }
+  return CRL_OK;
+}
+
+static int one_step(crl_engine_impl* e, int K) { return K <= 1 ? one_simulation(e) : one_wave(e, K); }
+
+// number of simulations the slowest game still has to run in the current wave-mode call (host sync)
+static int wave_left(crl_engine_impl* e, int* out) {
+  int* d_left = e->d_n + 2;
+  CRL_CUDA(cudaMemsetAsync(d_left, 0, sizeof(int), e->stream));
+  {
+    LaunchScope ls(e, KC_TREE);
+    k_wave_left<<<div_up(e->G, 256), 256, 0, e->stream>>>(e->P, d_left);
+    CRL_CUDA(cudaGetLastError());
+  }
+  CRL_CUDA(cudaMemcpyAsync(out, d_left, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));
+  return CRL_OK;
+}
+
 // The sequence is identical for every simulation (batch sizes live in device memory), so it is captured once
-// into a CUDA graph and replayed: one graph launch instead of ~55 kernel launches per simulation.
-int tree_simulate(crl_engine_impl* e, int n_sims) {
+// into a CUDA graph and replayed: one graph launch instead of ~10 kernel launches per simulation.
+// K = 1: n_sims lockstep simulations (the exact threads=1 schedule).  K > 1: waves of up to K simulations per game
+// until every running game has done n_sims; games whose waves were cut short need a few extra waves, found by
+// polling the device once per batch of waves.
+int tree_simulate(crl_engine_impl* e, int n_sims, int K) {
   if (n_sims <= 0) return CRL_OK;
+  if (K < 1) K = 1;
+  int n_steps = n_sims;
+  if (K > 1) {
+    LaunchScope ls(e, KC_TREE);
+    k_wave_begin<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, n_sims);
+    CRL_CUDA(cudaGetLastError());
+    n_steps = (n_sims + K - 1) / K;
+  }
+  for (;;) {
+    int rc = tree_run_steps(e, n_steps, K);
+    if (rc != CRL_OK) return rc;
+    if (K <= 1) return CRL_OK;
+    int left = 0;
+    rc = wave_left(e, &left);
+    if (rc != CRL_OK) return rc;
+    if (left <= 0) return CRL_OK;
+    n_steps = (left + K - 1) / K;
+  }
+}
+
+int tree_run_steps(crl_engine_impl* e, int n_sims, int K) {
   const bool graph_ok = e->use_graph && !e->profiling && e->stream != nullptr;
   if (!graph_ok) {
     for (int s = 0; s < n_sims; ++s) {
-      int rc = one_simulation(e);
+      int rc = one_step(e, K);
       if (rc != CRL_OK) return rc;
     }
     return CRL_OK;
   }
   const unsigned long long key = 1ull + (unsigned long long)e->eval_kind + 2ull * (unsigned long long)e->eval_bits +
-                                 64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull);
+                                 64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull) + 0x100000000ull * (unsigned long long)K;
   if (e->sim_graph == nullptr || e->sim_graph_key != key) {
     if (e->sim_graph) {
       cudaGraphExecDestroy(e->sim_graph);
       e->sim_graph = nullptr;
     }
     // run one simulation eagerly first: it creates whatever host-side state the launchers cache (tensor maps)
-    int rc = one_simulation(e);
+    int rc = one_step(e, K);
     if (rc != CRL_OK) return rc;
     --n_sims;
     const long long l0 = e->launches;
@@ -371,7 +537,7 @@ int tree_simulate(crl_engine_impl* e, int n_sims) {
     cudaGraph_t graph = nullptr;
     CRL_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     e->capturing = true;
-    rc = one_simulation(e);
+    rc = one_step(e, K);
     e->capturing = false;
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     e->sim_graph_launches = e->launches - l0;

@@ -1156,7 +1156,7 @@ static int dev_alloc(crl_engine_impl* e, T** p, size_t count) {
 int net_create(crl_engine_impl* e) {
   NetWeights* nw = new NetWeights();
   e->net = nw;
-  nw->cap_rows = (e->G + 2) & ~1;
+  nw->cap_rows = (e->R + 2) & ~1;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -1473,7 +1473,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
   }
   {
     // the box may start at row n-1 for an odd n: rows beyond the map are zero-filled by the TMA unit
-    const int rows = planes == e->d_planes ? e->G : n_host;
+    const int rows = planes == e->d_planes ? e->R : n_host;
     if (planes != nw->planes_ptr || rows != nw->planes_rows) {
       int rc = make_act_map(nw, &nw->map_planes, planes, 128, rows);
       if (rc) return rc;

@@ -386,6 +386,23 @@ CRL_HD int reply_child(const Pools& P, int g, int slot, int child, const float* 
   return KIND_EVAL_LEAF;
 }
 
+// wave mode, the serial part of one select (mctree.py:216-229): `what`/`node` come from select_descend_wave.
+// Fills scratch slot `slot`, adds the leaf's virtual loss, returns the slot's kind.
+CRL_HD int wave_take_slot(const Pools& P, int g, int slot, int what, int node) {
+  if (what == 1) {
+    P.s_node[slot] = node;
+    P.s_kind[slot] = KIND_TERMINAL;
+    vloss_add(P, g, node, 1);
+    return KIND_TERMINAL;
+  }
+  int child;
+  const int kind = expand_child(P, g, slot, node, &child);
+  P.s_node[slot] = child;
+  P.s_kind[slot] = kind;
+  if (kind != KIND_IDLE) vloss_add(P, g, child, 1);
+  return kind;
+}
+
 // cache the legal-order policy of an evaluated node on its edge slots (what _update_prior will hand out)
 CRL_HD void store_priors(const Pools& P, int g, int node, const float* policy_row, const int16_t* label_of) {
   const NodeRec& n = P.nodes[(long long)g * P.NN + node];

@@ -26,9 +26,10 @@ def _np(a, ctype):
 
 
 class Engine:
-    """max_games lockstep lanes, max_nodes tree nodes per game (>= simulations per move + 1)."""
+    """max_games lockstep lanes, max_nodes tree nodes per game (>= simulations per move + 1), max_inflight
+    in-flight simulations per game (the reference's `threads`; 1 = the exact threads=1 schedule only)."""
 
-    def __init__(self, max_games=1, max_nodes=1024, avg_moves=64, device=None):
+    def __init__(self, max_games=1, max_nodes=1024, avg_moves=64, device=None, max_inflight=1):
         if not torch.cuda.is_available():
             raise RuntimeError("chessrl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -36,11 +37,12 @@ class Engine:
         self.device = torch.device("cuda", self.device_index)
         self.max_games = int(max_games)
         self.max_nodes = int(max_nodes)
+        self.max_inflight = int(max_inflight)
         h = vp()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            check(self.lib.crl_create(ctypes.byref(h), self.device_index, self.max_games, self.max_nodes,
-                                      int(avg_moves), vp(stream)))
+            check(self.lib.crl_create_ex(ctypes.byref(h), self.device_index, self.max_games, self.max_nodes,
+                                         int(avg_moves), self.max_inflight, vp(stream)))
         self.h = h
         self.weights_loaded = False
 
@@ -163,18 +165,33 @@ class Engine:
     def set_evaluator(self, kind, seed=0, policy_bits=24):
         check(self.lib.crl_set_evaluator(self.h, int(kind), int(seed), int(policy_bits)))
 
-    def games_set(self, start_records, move_lists=None, first=0):
-        rec = np.ascontiguousarray(np.asarray(start_records, dtype=np.uint64).reshape(-1, 9))
-        n = rec.shape[0]
-        if move_lists is None:
-            check(self.lib.crl_games_set_host(self.h, first, n, _np(rec, ctypes.c_uint64), None, None, 0))
-            return
-        stride = max(1, max(len(m) for m in move_lists))
+    @staticmethod
+    def pack_move_lists(move_lists):
+        """list of per-game move-word lists -> (uint16 [n, stride], int32 [n]) host arrays for games_set."""
+        n = len(move_lists)
+        stride = max(1, max((len(m) for m in move_lists), default=1))
         mv = np.full((n, stride), B.MOVE_NONE, dtype=np.uint16)
         cnt = np.zeros(n, dtype=np.int32)
         for i, m in enumerate(move_lists):
             cnt[i] = len(m)
             mv[i, :len(m)] = m
+        return mv, cnt
+
+    def games_set(self, start_records, move_lists=None, first=0):
+        """Game(board) + Game.move for every listed move.  move_lists: per-game lists, or the packed pair from
+        pack_move_lists (host arrays; skips the per-game Python packing)."""
+        rec = np.ascontiguousarray(np.asarray(start_records, dtype=np.uint64).reshape(-1, 9))
+        n = rec.shape[0]
+        if move_lists is None:
+            check(self.lib.crl_games_set_host(self.h, first, n, _np(rec, ctypes.c_uint64), None, None, 0))
+            return
+        if isinstance(move_lists, tuple):
+            mv = np.ascontiguousarray(move_lists[0], dtype=np.uint16)
+            cnt = np.ascontiguousarray(move_lists[1], dtype=np.int32)
+            assert mv.ndim == 2 and mv.shape[0] == n and cnt.shape == (n,)
+        else:
+            mv, cnt = self.pack_move_lists(move_lists)
+        stride = mv.shape[1]
         check(self.lib.crl_games_set_host(self.h, first, n, _np(rec, ctypes.c_uint64), _np(mv, ctypes.c_uint16),
                                           _np(cnt, ctypes.c_int32), stride))
 

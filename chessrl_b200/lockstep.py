@@ -17,10 +17,17 @@ from ._lib import EVAL_NET
 
 def compute_policy(child_visits, root_visits, n_plies, noise=True):
     """SelfPlayTree.compute_policy (mctree.py:305-322) from the root statistics of one game."""
-    tau = 1
-    if n_plies >= 30:
+    if n_plies < 30:
+        # tau = 1: np.power(v, 1.0) is float(v) exactly, so the vectorised division is bit-identical
+        policy = np.asarray(child_visits, dtype=np.float64) / np.float64(int(root_visits))
+    else:
         tau = n_plies / (1 + np.power(n_plies, 1.3))
-    policy = np.array([np.power(int(v), 1 / tau) for v in child_visits]) / np.power(int(root_visits), 1 / tau)
+        memo = {}                       # the same scalar np.power call as the reference, once per distinct count
+        for v in child_visits:
+            v = int(v)
+            if v not in memo:
+                memo[v] = np.power(v, 1 / tau)
+        policy = np.array([memo[int(v)] for v in child_visits]) / np.power(int(root_visits), 1 / tau)
     if noise:
         epsilon = 0.25
         policy = (1 - epsilon) * policy + np.random.dirichlet([0.03] * len(child_visits))
@@ -33,12 +40,14 @@ class LockstepSelfPlay:
     colors: per-game player colour (True = the agent plays white).  When False the opponent opens with its
     policy-argmax move (selfplay.py:68-70).  noise=True draws Dirichlet noise from numpy's legacy global RNG in
     game-index order, once per game per move (the reference draws once per move of its single game).
+    inflight: simulations in flight per game (the reference's `threads`; needs Engine(max_inflight >= inflight)).
     """
 
-    def __init__(self, engine, n_games=None, sims=900, noise=True, refill=False):
+    def __init__(self, engine, n_games=None, sims=900, noise=True, refill=False, inflight=1):
         self.e = engine
         self.n = engine.max_games if n_games is None else n_games
         self.sims = sims
+        self.inflight = int(inflight)
         self.noise = noise
         self.refill = refill
         self.colors = np.ones(self.n, dtype=bool)
@@ -59,7 +68,7 @@ class LockstepSelfPlay:
         """One agent move (+ reply) for every running game.  Returns the (our move, reply) words [n, 2]."""
         e = self.e
         e.mcts_begin_move()
-        e.mcts_simulate(self.sims)
+        e.mcts_simulate(self.sims, self.inflight)
         st = e.root_stats(want=("visits",))
         _, plies, results = e.games_get(0, self.n)
         picks = np.full(e.max_games, -1, dtype=np.int32)

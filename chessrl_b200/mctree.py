@@ -3,10 +3,12 @@
 The tree of one game lives in the engine's flat node / edge pools on the GPU; Node objects here are read-only
 VIEWS built from crl_mcts_node_dump_host.  SelfPlayTree.search_move runs the reference's algorithm -- select,
 expand (our move + the opponent's policy-argmax reply), simulate (network value or game result), backprop -- for
-`max_iters` simulations with the deterministic threads=1 schedule, then picks the move on the host exactly as
-mctree.py:178-198 / 305-322 do (temperature, optional Dirichlet noise from numpy's global RNG, first argmax).
-`threads` is accepted for compatibility; with more than one thread the reference is schedule-dependent
-(SURVEY.md 5), the engine always runs the threads=1 order.
+`max_iters` simulations, then picks the move on the host exactly as mctree.py:178-198 / 305-322 do (temperature,
+optional Dirichlet noise from numpy's global RNG, first argmax).
+`threads` = simulations in flight: 1 is the reference's deterministic order; with K > 1 the reference is
+schedule-dependent and the engine runs one of its legal schedules deterministically -- waves of up to
+K selects (each adding its virtual loss), one evaluation batch, K backprops in the same order
+(include/chessrl_b200.h crl_mcts_simulate).
 """
 
 from __future__ import annotations
@@ -84,12 +86,13 @@ class SelfPlayTree(Tree):
 
     def search_move(self, agent, max_iters=200, verbose=False, noise=True, ai_move=False):
         game = self.root.state
-        eng = runtime.scalar_engine(min_nodes=max_iters + 1)
+        k = max(1, min(int(self.num_threads), 64))
+        eng = runtime.scalar_engine(min_nodes=max_iters + 1, min_inflight=k)
         self._engine = eng
         agent._bind_evaluator(eng)
         eng.games_set(game._start[None, :], [[B.uci_to_move(m) for m in game._moves]])
         eng.mcts_begin_move()
-        eng.mcts_simulate(max_iters)
+        eng.mcts_simulate(max_iters, inflight=k)
         self._refresh_views(eng)
         if not self.root.children:
             moves = (Game.NULL_MOVE, Game.NULL_MOVE)

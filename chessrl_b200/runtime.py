@@ -8,14 +8,16 @@ _scalar = None
 _loaded_token = None
 
 
-def scalar_engine(min_nodes=1024):
-    """The one-lane engine behind Game / netencoder / Agent / SelfPlayTree."""
+def scalar_engine(min_nodes=1024, min_inflight=1):
+    """The one-lane engine behind Game / netencoder / Agent / SelfPlayTree (grown on demand)."""
     global _scalar, _loaded_token
     from .engine import Engine
-    if _scalar is None or _scalar.max_nodes < min_nodes:
+    if _scalar is None or _scalar.max_nodes < min_nodes or _scalar.max_inflight < min_inflight:
+        nodes, inflight = max(1024, int(min_nodes)), max(8, int(min_inflight))
         if _scalar is not None:
+            nodes, inflight = max(nodes, _scalar.max_nodes), max(inflight, _scalar.max_inflight)
             _scalar.close()
-        _scalar = Engine(max_games=1, max_nodes=max(1024, int(min_nodes)), avg_moves=96)
+        _scalar = Engine(max_games=1, max_nodes=nodes, avg_moves=96, max_inflight=inflight)
         _loaded_token = None
     return _scalar
 

@@ -1,12 +1,13 @@
 """selfplay: drop-in for the reference's entry point (selfplay.py:111-167)
 
-    python -m chessrl_b200.selfplay modeldir [--games 1] [--threads 6] [--debug] [--sims 900] [--lanes N] [--no-train]
+    python -m chessrl_b200.selfplay modeldir [--games 1] [--threads 1] [--debug] [--sims 900] [--lanes N] [--no-train]
 
 Plays `--games` self-play games, appends them to <modeldir>/gameplays.json (README.md:77) and trains the model on
 them, saving the weights in place.  Unlike the reference, which plays one game at a time in a child process and
 talks to a prediction server over TCP, the games run in LOCKSTEP on the GPU (`--lanes` at a time, default all of
-them) and the "server" is the batched network evaluation inside the engine.  `--threads` is kept for
-compatibility (the search always uses the deterministic one-simulation-in-flight schedule); `--sims` exposes the
+them) and the "server" is the batched network evaluation inside the engine.  `--threads` = simulations in flight
+per game, like the reference's MCTS thread pool; its default here is 1 (the reference's only deterministic
+schedule) instead of 6, K > 1 runs the wave schedule (include/chessrl_b200.h).  `--sims` exposes the
 reference's hard-coded 900 simulations per move (selfplay.py:76).  With torchrun the games are sharded by rank,
 rank 0 broadcasts the weights and gathers the finished games (NCCL); there is no per-simulation collective.
 """
@@ -54,13 +55,15 @@ def play_game(agent, max_iters=900):
     return gam
 
 
-def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None):
+def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
+                        threads=1):
     """`n_games` games in lockstep; returns a DatasetGame.  The per-move host work is the numpy move policy only."""
     from ._lib import EVAL_NET
     from .engine import Engine
     from .lockstep import LockstepSelfPlay
     lanes = n_games if lanes is None else min(lanes, n_games)
-    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device)
+    threads = max(1, min(int(threads), 64))
+    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads)
     eng.load_weights(model.weights)
     eng.set_evaluator(EVAL_NET)
     rng = random.Random(seed)
@@ -68,7 +71,7 @@ def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device
     remaining = n_games
     while remaining > 0:
         n = min(lanes, remaining)
-        sp = LockstepSelfPlay(eng, n_games=n, sims=sims, noise=noise)
+        sp = LockstepSelfPlay(eng, n_games=n, sims=sims, noise=noise, inflight=threads)
         colors = [rng.random() >= 0.5 for _ in range(n)]
         sp.start(colors=colors)
         moves = 0
@@ -88,7 +91,8 @@ def main(argv=None):
     parser = argparse.ArgumentParser(description="Plays some chess games, stores the result and trains a model.")
     parser.add_argument('model_dir', metavar='modeldir', help="where to store (and load from) the trained model and the logs")
     parser.add_argument('--games', metavar='games', type=int, default=1)
-    parser.add_argument('--threads', metavar='threads', type=int, default=6)
+    parser.add_argument('--threads', metavar='threads', type=int, default=1,
+                        help="MCTS simulations in flight per game (reference default 6; 1 = its deterministic schedule)")
     parser.add_argument('--debug', action='store_true', default=False, help="Log debug messages on screen. Default false.")
     parser.add_argument('--sims', type=int, default=900, help="MCTS simulations per move (reference: 900)")
     parser.add_argument('--lanes', type=int, default=None, help="games stepped in lockstep per GPU")
@@ -112,7 +116,8 @@ def main(argv=None):
         sharding.broadcast_weights(agent.model)
     share = args.games // world + (1 if rank < args.games % world else 0)
     logger.info("rank %d/%d plays %d game(s), %d simulations per move" % (rank, world, share, args.sims))
-    data = play_games_lockstep(agent.model, share, sims=args.sims, lanes=args.lanes, device=local_rank) if share else DatasetGame()
+    data = (play_games_lockstep(agent.model, share, sims=args.sims, lanes=args.lanes, device=local_rank,
+                                threads=args.threads) if share else DatasetGame())
     if world > 1:
         from . import sharding
         data = sharding.gather_games(data)

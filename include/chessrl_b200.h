@@ -42,6 +42,7 @@ extern "C" {
 #define CRL_RESULT_NONE 2
 #define CRL_MOVE_NONE 0xFFFF
 #define CRL_N_WEIGHT_TENSORS 140
+#define CRL_MAX_INFLIGHT 64
 
 typedef enum {
   CRL_OK = 0,
@@ -62,6 +63,11 @@ typedef struct crl_engine crl_engine;
 /* max_games: lockstep lanes; max_nodes: tree nodes per game (>= sims per move + 1); avg_moves: edge-pool
  * sizing hint (edges per game = max_nodes * avg_moves, 0 -> 64); stream: cudaStream_t or NULL. */
 int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, void* stream);
+/* max_inflight (1..CRL_MAX_INFLIGHT): in-flight simulations per game the evaluation workspaces are sized for =
+ * the reference's `threads` (SelfPlayTree(root, threads), mctree.py:155-157; selfplay.py --threads, default 6).
+ * crl_create == crl_create_ex(..., 1, stream). */
+int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, int max_inflight,
+                  void* stream);
 int crl_destroy(crl_engine* e);
 const char* crl_last_error(void);
 int crl_version(void);
@@ -132,8 +138,14 @@ int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t
 /* Tree(root) (mctree.py:104-111): a fresh tree per running game rooted at its current position,
  * root.visits = 1, root evaluated once for its children's priors. */
 int crl_mcts_begin_move(crl_engine* e);
-/* n_sims x SelfPlayTree.explore_tree (mctree.py:200-214) for every running game in lockstep.  inflight = 1 is
- * the deterministic threads=1 schedule (the only one implemented in this round). */
+/* n_sims x SelfPlayTree.explore_tree (mctree.py:200-214) for every running game in lockstep.
+ * inflight = 1: the deterministic threads=1 schedule.
+ * inflight = K > 1 (<= max_inflight): WAVES of up to K simulations per game = one legal schedule of the reference's
+ * ThreadPoolExecutor(max_workers=K) (mctree.py:173-176): the wave's selects run one after the other (each adds its
+ * virtual loss to its leaf, mctree.py:226-227), then its evaluations as one batch, then its backprops in the same
+ * order (mctree.py:278-296, virtual loss removed).  A select that would enter a node created earlier in the same
+ * wave (whose opponent reply is still being evaluated) is deferred to the next wave.  Deterministic; every game
+ * runs exactly n_sims simulations. */
 int crl_mcts_simulate(crl_engine* e, int n_sims, int inflight);
 /* root children in creation order (mctree.py:305-322 needs visits): arrays [n_games][CRL_MAX_MOVES] except
  * n_children/root_visits/root_ply [n_games]; any may be NULL */

@@ -210,7 +210,13 @@ class OAgent:
 
 
 # --------------------------------------------------------------------------
-# mctree.py (threads=1 schedule: one in-flight simulation)
+# mctree.py.  threads=1: one in-flight simulation (deterministic in the reference).
+# threads=K>1: the reference is schedule-dependent; the oracle runs the WAVE schedule --
+# up to K selects one after the other (each adds its virtual loss), then their simulates, then their backprops
+# in the same order -- which is one legal interleaving of ThreadPoolExecutor(max_workers=K) (mctree.py:173-176).
+# A select that would enter a node created earlier in the same wave by an expansion that needed the opponent's
+# reply is deferred to the next wave (legal too: "that worker had not started yet"); the lockstep engine needs
+# this because the reply comes out of the wave's own evaluation batch.
 # --------------------------------------------------------------------------
 
 class ONode:
@@ -225,6 +231,7 @@ class ONode:
         self.visits = 0
         self.prior = 1
         self.vloss = 0
+        self.pending = False       # wave schedule only: created in the current wave with an opponent reply
         self._result_known = False
         self._result = None
 
@@ -249,15 +256,22 @@ class ONode:
 
 
 class OSelfPlayTree:
-    """mctree.SelfPlayTree (mctree.py:148-322) restated for the deterministic threads=1 schedule."""
+    """mctree.SelfPlayTree (mctree.py:148-322) restated: threads=1 (deterministic) or the wave schedule."""
 
-    def __init__(self, root):
+    def __init__(self, root, threads=1):
         self.root = root if isinstance(root, ONode) else ONode(root.get_copy())  # mctree.py:106-109
         self.root.visits = 1                                                      # mctree.py:111
+        self.num_threads = threads                                                # mctree.py:157
+        self.n_waves = 0
 
     def search_move(self, agent, max_iters=200, noise=True, ai_move=False):       # mctree.py:159-198
-        for _ in range(max_iters):
-            self.explore_tree(agent)
+        if self.num_threads <= 1:
+            for _ in range(max_iters):
+                self.explore_tree(agent)
+        else:
+            left = max_iters
+            while left > 0:
+                left -= self.explore_wave(agent, min(self.num_threads, left))
         pick = int(np.argmax(self.compute_policy(self.root, noise=noise)))
         stack = self.root.children[pick].state.board.move_stack
         ours = str(stack[-2]) if len(stack) >= 2 else NULL_MOVE
@@ -268,6 +282,30 @@ class OSelfPlayTree:
         leaf = self.select(agent)
         v = self.simulate(leaf, agent)
         self.backprop(leaf, v)
+
+    def explore_wave(self, agent, k):
+        """Up to k explore_tree calls interleaved as select*, simulate*, backprop* (see the header comment)."""
+        leaves = []
+        for j in range(k):
+            if j and self._next_select_meets_pending():
+                break
+            leaves.append(self.select(agent))
+        values = [self.simulate(leaf, agent) for leaf in leaves]
+        for leaf, v in zip(leaves, values):
+            leaf.pending = False
+            self.backprop(leaf, v)
+        self.n_waves += 1
+        return len(leaves)
+
+    def _next_select_meets_pending(self):
+        node = self.root                                                          # a dry run of select: pure
+        while not node.is_terminal_state:
+            if node.unexpanded_actions:
+                return False
+            node = node.get_best_child()
+            if node.pending:
+                return True
+        return False
 
     def select(self, agent):                                                      # mctree.py:216-229
         node = self.root
@@ -282,9 +320,11 @@ class OSelfPlayTree:
     def expand(self, node, agent):                                                # mctree.py:231-257
         state = node.state.get_copy()
         state.move(node.unexpanded_actions.pop())                                 # last legal move first
-        if state.get_result() is None:
+        replied = state.get_result() is None
+        if replied:
             state.move(agent.policy_move(state))                                  # opponent = policy argmax
         child = ONode(state, parent=node)
+        child.pending = replied and self.num_threads > 1
         node.children.append(child)
         if not node.unexpanded_actions:                                           # mctree.py:254-255, 298-303
             for p, c in zip(agent.predict_policy(node.state), reversed(node.children)):

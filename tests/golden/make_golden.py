@@ -153,6 +153,85 @@ def gen_mcts(ref):
                    "cases": cases}, f)
 
 
+def ref_wave_search(tree, agent, sims, K):
+    """Drives the reference's own SelfPlayTree.select / simulate / backprop (mctree.py:216-296) in the WAVE
+    schedule of threads=K (see oracle/chessrl_oracle.py): per wave up to K selects, then their simulates, then
+    their backprops in the same order; a select that would enter a node created in the same wave by an expansion
+    with an opponent reply is deferred to the next wave.  Returns the number of waves."""
+    def meets_pending(pending):
+        node = tree.root
+        while not node.is_terminal_state:                 # dry run of select: these reference calls are pure
+            if not node.is_fully_expanded:
+                return False
+            node = node.get_best_child()
+            if id(node) in pending:
+                return True
+        return False
+
+    left, waves = sims, 0
+    while left > 0:
+        leaves, pending = [], set()
+        for j in range(min(K, left)):
+            if j and meets_pending(pending):
+                break
+            leaf = tree.select(tree.root, agent)
+            new = leaf.visits == 0 and all(leaf is not x for x in leaves)
+            if new and len(leaf.state.board.move_stack) == len(leaf.parent.state.board.move_stack) + 2:
+                pending.add(id(leaf))
+            leaves.append(leaf)
+        values = [tree.simulate(leaf, agent) for leaf in leaves]
+        for leaf, v in zip(leaves, values):
+            tree.backprop(leaf, v, remove_vloss=True)
+        left -= len(leaves)
+        waves += 1
+    return waves
+
+
+def gen_mcts_wave(ref):
+    """threads=K > 1: the reference's own select / simulate / backprop driven in the wave schedule."""
+    cases = []
+    roots = [("start", None, []), ("kiwipete", FENS["kiwipete"], []), ("pos3", FENS["pos3"], []),
+             ("pos4", FENS["pos4"], []), ("mate_in_1", FENS["mate_in_1"], []), ("kq_vs_k", FENS["kq_vs_k"], []),
+             ("black_to_move_mates", FENS["black_to_move_mates"], []), ("fifty_near", FENS["fifty_near"], []),
+             ("random11_24", None, random_game_moves(ref, 11, 24)),
+             ("random13_80", None, random_game_moves(ref, 13, 80)),
+             # narrow trees (1-3 legal moves per node): nodes fill up inside one wave, so waves get cut
+             ("narrow_one_move", "k7/8/8/8/8/8/1r6/K7 w - - 0 1", []),
+             ("narrow_two_moves", "8/8/8/8/8/2k5/7p/K7 w - - 0 1", []),
+             ("narrow_pawn_ending", "8/8/8/p7/P7/8/8/K6k w - - 0 1", []),
+             ("narrow_check_evasion", "4k3/8/8/8/8/8/4r3/4K3 w - - 0 1", [])]
+    for name, fen, moves in roots:
+        for seed, bits in ((1, 24), (2, 3)):
+            plan = ((2, 40), (6, 120), (8, 100), (16, 150))
+            if name.startswith("narrow"):
+                plan = ((3, 60), (6, 90), (32, 128), (64, 128))
+            for K, sims in plan:
+                board = ref.chess.Board(fen) if fen else ref.chess.Board()
+                g = ref.game.Game(board=board)
+                for m in moves:
+                    assert g.move(m)
+                if g.get_result() is not None:
+                    continue
+                ev = O.hash_evaluator(seed=seed, policy_bits=bits)
+                agent = ref_on_shims.make_ref_agent(ref, ev)
+                type(agent).n_evals = 0
+                tree = ref.mctree.SelfPlayTree(g, threads=K)
+                waves = ref_wave_search(tree, agent, sims, K)
+                assert all(c.vloss == 0 for c in tree.root.children)
+                pick = int(np.argmax(tree.compute_policy(tree.root, noise=False)))
+                st = tree.root.children[pick].state.board.move_stack
+                ret = (str(st[-2]), str(st[-1])) if len(st) >= 2 else ("00000", "00000")
+                rec = dump_tree(tree, type(agent).n_evals, ret)
+                rec.update({"name": name, "fen": fen, "moves": moves, "eval_seed": seed, "policy_bits": bits,
+                            "sims": sims, "threads": K, "waves": waves})
+                cases.append(rec)
+    with open(os.path.join(OUT, "mcts_wave.json"), "w") as f:
+        json.dump({"source": "mctree.SelfPlayTree(threads=K).select / simulate / backprop (mctree.py:216-296), the "
+                             "reference's own methods driven in the wave schedule (make_golden.ref_wave_search); "
+                             "evaluator = chessrl_oracle.hash_evaluator(seed, policy_bits)",
+                   "cases": cases}, f)
+
+
 def gen_toy(ref):
     """the reference mctree.py on a toy game (no chess rules involved)."""
 
@@ -296,6 +375,7 @@ def main():
     gen_toy(ref)
     gen_rules(ref)
     gen_mcts(ref)
+    gen_mcts_wave(ref)
     gen_selfplay(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))

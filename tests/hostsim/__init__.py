@@ -7,11 +7,12 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_hostsim.so")
 _SRC = os.path.join(_HERE, "hostsim.cpp")
-_CORE = os.path.join(_HERE, "..", "..", "chessrl_b200", "csrc", "chess_core.cuh")
+_CSRC = os.path.join(_HERE, "..", "..", "chessrl_b200", "csrc")
+_DEPS = [os.path.join(_CSRC, f) for f in ("chess_core.cuh", "tree_core.cuh", "hash_eval.cuh")]
 
 
 def load():
-    newest = max(os.path.getmtime(_SRC), os.path.getmtime(_CORE))
+    newest = max([os.path.getmtime(_SRC)] + [os.path.getmtime(d) for d in _DEPS])
     if not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++", _SRC, "-o", _SO])
     lib = ctypes.CDLL(_SO)

@@ -92,10 +92,12 @@ struct HostTree {
 
 extern "C" {
 
+enum { HS_KMAX = 64 };
+
 void* hs_tree_new(int NN, int EA, const int16_t* label_of) {
   HostTree* t = new HostTree();
   Pools& P = t->P;
-  P.G = 1; P.NN = NN; P.EA = EA;
+  P.G = 1; P.NN = NN; P.EA = EA; P.K = 1;
   P.g_cur = (u64*)calloc(9, 8);
   P.g_hist = (u64*)calloc(HIST_RING * 8, 8);
   P.g_keys = (u64*)calloc(KEY_RING, 8);
@@ -112,14 +114,17 @@ void* hs_tree_new(int NN, int EA, const int16_t* label_of) {
   P.e_value = (double*)calloc(EA, 8);
   P.e_child = (int*)calloc(EA, 4);
   P.e_result = (int8_t*)calloc(EA, 1);
+  P.e_vloss = (u8*)calloc(EA, 1);
   P.r_visits = (int*)calloc(1, 4);
   P.r_value = (double*)calloc(1, 8);
-  P.s_node = (int*)calloc(1, 4);
-  P.s_kind = (int*)calloc(1, 4);
-  P.s_moves = (u16*)calloc(MAX_MOVES, 2);
-  P.s_nmoves = (int*)calloc(1, 4);
-  P.s_row = (int*)calloc(1, 4);
-  P.eval_list = (int*)calloc(1, 4);
+  P.s_node = (int*)calloc(HS_KMAX, 4);
+  P.s_kind = (int*)calloc(HS_KMAX, 4);
+  P.s_moves = (u16*)calloc(HS_KMAX * MAX_MOVES, 2);
+  P.s_nmoves = (int*)calloc(HS_KMAX, 4);
+  P.s_row = (int*)calloc(HS_KMAX, 4);
+  P.s_wave_n = (int*)calloc(1, 4);
+  P.g_sims_left = (int*)calloc(1, 4);
+  P.eval_list = (int*)calloc(HS_KMAX, 4);
   P.eval_n = (int*)calloc(1, 4);
   P.err = (int*)calloc(1, 4);
   P.counters = (long long*)calloc(4, 8);
@@ -165,12 +170,12 @@ int hs_search(void* h, int sims, uint64_t seed, int bits) {
       val = (double)P.nodes[node].result;
     } else {
       int child;
-      int kind = expand_child(P, 0, node, &child);
+      int kind = expand_child(P, 0, 0, node, &child);
       node = child;
       if (kind == KIND_NEED_REPLY) {
         host_eval(t, P.nodes[child].p1, seed, bits, &v);
         ++evals;
-        kind = reply_child(P, 0, child, t->policy.data(), t->label_of.data());
+        kind = reply_child(P, 0, 0, child, t->policy.data(), t->label_of.data());
       }
       if (kind == KIND_EVAL_LEAF) {
         host_eval(t, P.nodes[child].p2, seed, bits, &v);
@@ -184,6 +189,55 @@ int hs_search(void* h, int sims, uint64_t seed, int bits) {
     backup(P, 0, node, val);
   }
   return evals | (*P.err << 24);
+}
+
+// wave mode (K in-flight simulations): the same three phases as k_select_wave / k_reply / k_finalize_wave, serially
+int hs_search_wave(void* h, int sims, int K, uint64_t seed, int bits) {
+  HostTree* t = (HostTree*)h;
+  Pools& P = t->P;
+  if (K > HS_KMAX) return -1;
+  P.K = K;
+  float v;
+  root_init(P, 0);
+  host_eval(t, P.nodes[0].p2, seed, bits, &v);
+  store_priors(P, 0, 0, t->policy.data(), t->label_of.data());
+  int evals = 1, left = sims, waves = 0;
+  std::vector<double> vals(K);
+  while (left > 0) {
+    const int kmax = left < K ? left : K;
+    int used = 0;
+    for (int j = 0; j < kmax; ++j) {
+      int node = 0;
+      int what = select_descend_wave(P, 0, [&](const NodeRec& n) { return best_edge_serial(P, 0, n, true); }, &node);
+      if (what == 2) break;
+      wave_take_slot(P, 0, used, what, node);
+      ++used;
+    }
+    for (int j = 0; j < used; ++j) {
+      if (P.s_kind[j] != KIND_NEED_REPLY) continue;
+      host_eval(t, P.nodes[P.s_node[j]].p1, seed, bits, &v);
+      ++evals;
+      P.s_kind[j] = reply_child(P, 0, j, P.s_node[j], t->policy.data(), t->label_of.data());
+    }
+    for (int j = 0; j < used; ++j) {
+      const int node = P.s_node[j];
+      double val;
+      if (P.s_kind[j] == KIND_EVAL_LEAF) {
+        host_eval(t, P.nodes[node].p2, seed, bits, &v);
+        ++evals;
+        store_priors(P, 0, node, t->policy.data(), t->label_of.data());
+        val = (double)v;
+      } else {
+        val = (double)P.nodes[node].result;
+      }
+      backup(P, 0, node, val);
+      vloss_add(P, 0, node, -1);
+    }
+    left -= used;
+    ++waves;
+  }
+  P.K = 1;
+  return waves | (*P.err << 24);
 }
 
 // root stats in child creation order

@@ -66,6 +66,73 @@ def test_mcts_golden_all_cases_in_lockstep(golden_dir):
         e.close()
 
 
+def test_mcts_wave_golden_all_cases_in_lockstep(golden_dir):
+    """threads=K > 1 (wave schedule with virtual loss): bit-exact against the reference's own select / simulate /
+    backprop driven in that schedule; cases sharing (evaluator, sims, K) run as lanes of one engine, so lanes whose
+    waves get cut (narrow trees) run next to lanes that never are."""
+    from chessrl_b200.engine import Engine
+    cases = json.load(open(os.path.join(golden_dir, "mcts_wave.json")))["cases"]
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["eval_seed"], c["policy_bits"], c["sims"], c["threads"]), []).append(c)
+    assert len(cases) >= 100
+    for (seed, bits, sims, K), cs in groups.items():
+        e = Engine(max_games=len(cs), max_nodes=sims + 1, avg_moves=96, max_inflight=K)
+        e.set_evaluator(EVAL_HASH, seed, bits)
+        recs = np.stack([B.record_from_fen(c["fen"] or B.STARTING_FEN) for c in cs])
+        mls = [[B.uci_to_move(m) for m in c["moves"]] for c in cs]
+        e.games_set(recs, mls)
+        e.mcts_begin_move()
+        e.mcts_simulate(sims, inflight=K)
+        st = e.root_stats()
+        picks = np.full(len(cs), -1, dtype=np.int32)
+        for g, c in enumerate(cs):
+            picks[g] = _check_case(c, st, g, None)
+        out = e.commit(picks, apply=False)
+        for g, c in enumerate(cs):
+            assert [B.move_to_uci(out[g, 0]), B.move_to_uci(out[g, 1])] == c["returned"], (c["name"], sims, K)
+        assert e.counters()["simulations"] == sims * len(cs)
+        # the same engine still runs the exact schedule afterwards (scratch indexing switches back to K = 1)
+        e.mcts_begin_move()
+        e.mcts_simulate(min(sims, 30))
+        assert (e.root_stats(want=("visits",))["root_visits"] == min(sims, 30) + 1).all()
+        e.close()
+
+
+def test_wave_mode_against_oracle_many_lanes():
+    """64 different midgame positions x K = 6 (the reference's default thread count) against the oracle's wave
+    schedule, all lanes in one engine."""
+    import random
+    from chessrl_b200.engine import Engine
+    rng = random.Random(7)
+    games = []
+    for _ in range(64):
+        g = O.OGame()
+        for _ in range(rng.randrange(4, 40)):
+            if g.get_result() is not None:
+                break
+            legal = g.get_legal_moves()
+            g.move(legal[rng.randrange(len(legal))])
+        if g.get_result() is None:
+            games.append(g)
+    K, sims = 6, 50
+    e = Engine(max_games=len(games), max_nodes=sims + 1, avg_moves=96, max_inflight=K)
+    e.set_evaluator(EVAL_HASH, 21, 24)
+    e.games_set(np.tile(B.record_from_fen(), (len(games), 1)),
+                [[B.uci_to_move(str(m)) for m in g.board.move_stack] for g in games])
+    e.mcts_begin_move()
+    e.mcts_simulate(sims, inflight=K)
+    st = e.root_stats()
+    for lane, g in enumerate(games):
+        ot = O.OSelfPlayTree(g, threads=K)
+        ot.search_move(O.OAgent(O.hash_evaluator(21, 24)), max_iters=sims, noise=False)
+        n = len(ot.root.children)
+        assert int(st["n_children"][lane]) == n
+        assert list(st["visits"][lane, :n]) == [c.visits for c in ot.root.children], lane
+        assert [float(x) for x in st["values"][lane, :n]] == [float(c.value) for c in ot.root.children], lane
+    e.close()
+
+
 def test_node_dump_matches_oracle_tree(engine1):
     g = O.OGame()
     for m in ["d2d4", "g8f6", "c2c4", "e7e6"]:

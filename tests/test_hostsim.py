@@ -26,6 +26,7 @@ def lib():
     L.hs_tree_new.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int16)]
     L.hs_game_set.argtypes = [ctypes.c_void_p, u64p, u16p, ctypes.c_int]
     L.hs_search.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+    L.hs_search_wave.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
     L.hs_root_stats.argtypes = [ctypes.c_void_p, i32p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float),
                                 u16p, u16p, i32p, i32p, ctypes.POINTER(ctypes.c_double)]
     L.hs_grandchild_visits.argtypes = [ctypes.c_void_p, ctypes.c_int, i32p]
@@ -115,6 +116,37 @@ def test_device_tree_core_matches_reference_mcts(lib, golden_dir):
             line = [B.move_to_uci(M[k])] + ([B.move_to_uci(R[k])] if R[k] != 0xFFFF else [])
             assert line == kid["line"]
             assert V[k] == kid["visits"] and W[k] == float.fromhex(kid["value"])
+            assert (None if Rs[k] == 2 else Rs[k]) == kid["result"]
+            G = (ctypes.c_int * 256)()
+            ng = lib.hs_grandchild_visits(t, k, G)
+            assert [G[j] for j in range(ng)] == kid["grandchild_visits"]
+            if float.fromhex(kid["prior"]) != 1.0:
+                assert Pr[k] == float.fromhex(kid["prior"])
+                assert lib.hs_edge_score(V[k], W[k], Pr[k], Rs[k]) == float.fromhex(kid["score"])
+
+
+def test_device_tree_core_wave_mode_matches_reference(lib, golden_dir):
+    """threads=K > 1 (wave schedule, virtual loss): the device tree code against the reference-driven golden."""
+    tab = _label_table()
+    t = lib.hs_tree_new(1024, 1024 * 64, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    cases = json.load(open(os.path.join(golden_dir, "mcts_wave.json")))["cases"]
+    assert len(cases) >= 60
+    for c in cases:
+        rec = B.record_from_fen(c["fen"] or B.STARTING_FEN)
+        mv = np.array([B.uci_to_move(m) for m in c["moves"]], dtype=np.uint16)
+        assert lib.hs_game_set(t, rec.ctypes.data_as(u64p), mv.ctypes.data_as(u16p), len(mv)) == len(mv)
+        w = lib.hs_search_wave(t, c["sims"], c["threads"], c["eval_seed"], c["policy_bits"])
+        assert w >> 24 == 0 and (w & 0xFFFFFF) == c["waves"], (c["name"], c["threads"], w, c["waves"])
+        V, W, Pr = (ctypes.c_int * 256)(), (ctypes.c_double * 256)(), (ctypes.c_float * 256)()
+        M, R, Rs = (ctypes.c_uint16 * 256)(), (ctypes.c_uint16 * 256)(), (ctypes.c_int * 256)()
+        rv, rw = ctypes.c_int(), ctypes.c_double()
+        n = lib.hs_root_stats(t, V, W, Pr, M, R, Rs, ctypes.byref(rv), ctypes.byref(rw))
+        kids = c["children"]
+        assert n == len(kids) and rv.value == c["root_visits"] and rw.value == float.fromhex(c["root_value"])
+        for k, kid in enumerate(kids):
+            line = [B.move_to_uci(M[k])] + ([B.move_to_uci(R[k])] if R[k] != 0xFFFF else [])
+            assert line == kid["line"]
+            assert V[k] == kid["visits"] and W[k] == float.fromhex(kid["value"]), (c["name"], c["threads"], k)
             assert (None if Rs[k] == 2 else Rs[k]) == kid["result"]
             G = (ctypes.c_int * 256)()
             ng = lib.hs_grandchild_visits(t, k, G)

@@ -136,6 +136,38 @@ def test_mcts_chess_golden(golden_dir):
         assert len(t.root.children) == len(c["children"])
 
 
+def test_mcts_wave_golden(golden_dir):
+    """threads=K > 1: the oracle's wave schedule against the reference's own select / simulate / backprop driven
+    in that schedule (tests/golden/make_golden.py ref_wave_search)."""
+    cases = json.load(open(os.path.join(golden_dir, "mcts_wave.json")))["cases"]
+    ran = 0
+    for c in cases:
+        if c["sims"] > 100 or c["policy_bits"] != 24:
+            continue                                   # the rest run in the hostsim / GPU parity tests
+        ag = O.OAgent(O.hash_evaluator(c["eval_seed"], c["policy_bits"]))
+        t = O.OSelfPlayTree(_game(c["fen"], c["moves"]), threads=c["threads"])
+        ret = t.search_move(ag, max_iters=c["sims"], noise=False, ai_move=True)
+        assert list(ret) == c["returned"], c["name"]
+        assert t.n_waves == c["waves"]
+        assert t.root.visits == c["root_visits"] and float(t.root.value) == float.fromhex(c["root_value"])
+        assert len(t.root.children) == len(c["children"])
+        for k, kid in zip(t.root.children, c["children"]):
+            assert k.visits == kid["visits"] and float(k.value) == float.fromhex(kid["value"]) and k.vloss == 0
+            assert [g.visits for g in k.children] == kid["grandchild_visits"]
+            assert float(k.get_value()) == float.fromhex(kid["score"])
+        ran += 1
+    assert ran >= 10
+
+
+def test_wave_schedule_threads1_is_the_plain_schedule():
+    g = _game(None, ["e2e4", "e7e5"])
+    a = O.OSelfPlayTree(g, threads=1)
+    a.search_move(O.OAgent(O.hash_evaluator(3, 24)), max_iters=40, noise=False)
+    b = O.OSelfPlayTree(g)
+    b.search_move(O.OAgent(O.hash_evaluator(3, 24)), max_iters=40, noise=False)
+    assert [c.visits for c in a.root.children] == [c.visits for c in b.root.children]
+
+
 def test_selfplay_golden(golden_dir):
     for run in json.load(open(os.path.join(golden_dir, "selfplay.json")))["runs"]:
         ag = O.OAgent(O.hash_evaluator(run["eval_seed"]))
