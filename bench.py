@@ -161,6 +161,128 @@ def perft_metric(engine):
     return out
 
 
+def _time_launch(fn, flush, reps=5):
+    """Mean CUDA-event time (ms) of `fn` (one launch), L2 flushed before every timed launch, 3 warm-ups."""
+    import torch
+    for _ in range(3):
+        fn()
+    tot = 0.0
+    for _ in range(reps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / reps
+
+
+def kernel_rooflines(engine, peaks, flush, net_loaded):
+    """Per-kernel achieved throughput against its roofline (SURVEY.md 8(d) algorithmic bytes / FLOPs per unit),
+    each kernel timed alone through the C ABI on device-resident inputs larger than L2 or after an L2 flush."""
+    import torch
+    from chessrl_b200 import boards as B
+    out = {}
+    hbm = peaks["hbm_gbs"]
+    # ~1M midgame boards: Kiwipete's depth-3 frontier (97,862 boards) replicated 11 times
+    fr = engine.boards_to_device(B.record_from_fen(KIWI)[None, :])
+    for _ in range(3):
+        fr, _ = engine.expand_frontier(fr)
+    boards = fr.repeat(1, 11).contiguous()
+    n = boards.shape[1]
+    moves = torch.empty((n, B.MAX_MOVES), dtype=torch.int16, device=engine.device)
+    counts = torch.empty((n,), dtype=torch.int32, device=engine.device)
+    from chessrl_b200.engine import _ptr
+    from chessrl_b200._lib import check
+    ms = _time_launch(lambda: check(engine.lib.crl_movegen(engine.h, _ptr(boards), n, _ptr(moves), _ptr(counts), None)), flush)
+    avg_l = float(counts.float().mean().item())
+    byt = n * (72 + 2 * avg_l + 4)
+    out["movegen"] = {"bound": "issue slots (INT64), then hbm", "boards": n, "avg_legal_moves": avg_l, "us": ms * 1e3,
+                      "boards_per_s": n / ms * 1e3, "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                      "frac": byt / ms / 1e6 / hbm, "algorithmic_bytes_per_board": 72 + 2 * avg_l + 4}
+    first = moves[:, 0].contiguous()
+    work = boards.clone()
+    ms = _time_launch(lambda: check(engine.lib.crl_make_moves(engine.h, _ptr(work), n, _ptr(first))), flush)
+    out["make_move"] = {"bound": "hbm", "boards": n, "us": ms * 1e3, "moves_per_s": n / ms * 1e3,
+                        "achieved": n * 146 / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": n * 146 / ms / 1e6 / hbm,
+                        "algorithmic_bytes_per_move": 146}
+    # encode: 32,768 positions with a full 8-position history (580 B in, 16,384 B out per position)
+    ne = 32768
+    eb = boards[:, :ne].contiguous()
+    hist = boards[:8, :8 * ne].reshape(8, 8, ne).contiguous()      # any bitboards do: the kernel's traffic is what counts
+    hl = torch.full((ne,), 8, dtype=torch.uint8, device=engine.device)
+    planes = torch.empty((ne, 8, 8, 128), dtype=torch.bfloat16, device=engine.device)
+    ms = _time_launch(lambda: check(engine.lib.crl_encode(engine.h, _ptr(eb), _ptr(hist), _ptr(hl), ne, _ptr(planes))), flush)
+    byt = ne * (580 + 16384)
+    out["encode"] = {"bound": "hbm", "positions": ne, "us": ms * 1e3, "positions_per_s": ne / ms * 1e3,
+                     "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s", "frac": byt / ms / 1e6 / hbm,
+                     "algorithmic_bytes_per_position": 580 + 16384}
+    del planes, hist
+    if net_loaded:
+        # BASELINE configs[2]: encode + network evaluation, 4,096 positions per batch, 3 distinct batches rotated
+        nb = 4096
+        batches = []
+        for k in range(3):
+            bb = boards[:, k * nb:(k + 1) * nb].contiguous()
+            hh = boards[:8, (3 + 8 * k) * nb:(3 + 8 * k + 8) * nb].reshape(8, 8, nb).contiguous()
+            batches.append((bb, hh, torch.full((nb,), 8, dtype=torch.uint8, device=engine.device),
+                            torch.empty((nb, 8, 8, 128), dtype=torch.bfloat16, device=engine.device),
+                            torch.empty((nb, 1968), dtype=torch.float32, device=engine.device),
+                            torch.empty((nb,), dtype=torch.float32, device=engine.device)))
+
+        def one(k):
+            bb, hh, ll, pl, po, va = batches[k % 3]
+            check(engine.lib.crl_encode(engine.h, _ptr(bb), _ptr(hh), _ptr(ll), nb, _ptr(pl)))
+            check(engine.lib.crl_net_forward(engine.h, _ptr(pl), nb, _ptr(po), _ptr(va)))
+        for k in range(3):
+            one(k)
+        torch.cuda.synchronize()
+        reps = 30
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in range(reps):
+            one(k)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        tf = nb * NET_FLOP_PER_POS / ms / 1e9
+        out["encode_plus_net"] = {"bound": "tensor", "workload": "BASELINE configs[2]: 4,096 positions per batch, encode + "
+                                  "policy/value network, 3 distinct batches rotated, 30 back-to-back evaluations",
+                                  "positions_per_s": nb / ms * 1e3, "ms_per_batch": ms, "achieved": tf,
+                                  "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                  "frac": tf / peaks["bf16_tflops_sustained"]}
+    return out
+
+
+def cpu_perft_baseline():
+    """Single-core perft(3) of the start position and Kiwipete on the python-chess restatement."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chessrl_oracle as O
+    chess = O.chess
+
+    def perft(board, d):
+        if d == 0:
+            return 1
+        n = 0
+        for m in board.generate_legal_moves():
+            board.push(m)
+            n += perft(board, d - 1)
+            board.pop()
+        return n
+    out = {}
+    for name, fen, want in (("start", None, 8902), ("kiwipete", KIWI, 97862)):
+        b = chess.Board(fen) if fen else chess.Board()
+        t0 = time.perf_counter()
+        got = perft(b, 3)
+        dt = time.perf_counter() - t0
+        assert got == want, (name, got, want)
+        out[name] = {"depth": 3, "nodes": got, "nodes_per_s": got / dt}
+    out["cores"] = 1
+    out["kind"] = "port (python-chess 0.28.3 restatement, pure Python)"
+    return out
+
+
 def cpu_reference_sims(budget_s, sims_per_move, seed=0):
     """The reference path on the host cores: oracle restatement of selfplay.play_game / mctree (threads=1) with the
     torch-CPU fp32 network, 1 game from the start position, `sims_per_move` simulations per move, for about
@@ -239,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-perft", action="store_true")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -366,23 +489,30 @@ def main():
             flop_per_launch = evals * CONV_FLOP_PER_POS / conv["launches"]
             t_launch = conv["ms"] * 1e-3 / conv["launches"]
             achieved = flop_per_launch / t_launch / 1e12
-            roof = {"bound": "tensor", "kernel": "k_conv_v2 (tcgen05 cta_group::2 implicit-GEMM 3x3 convolution)", "achieved": achieved,
+            roof = {"bound": "tensor", "kernel": "k_trunk (the 21 tcgen05 cta_group::2 implicit-GEMM 3x3 convolutions of the residual "
+                    "tower as ONE persistent CTA-pair kernel)", "achieved": achieved,
                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4,096 positions, mean of 4 captured
-                    # launches (profiles/r01_ncu_conv_v2.txt); algorithmic: 134 MB in + 134 MB out (+134 MB residual on every
-                    # second layer) + 1.2 MB weights -- the write-back of the last wave is still in L2 when the launch ends
-                    "traffic": 288.3e6 if G == 4096 else None, "traffic_unit": "bytes/launch",
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4,096 positions, mean of 2 captured
+                    # launches (profiles/r01_ncu_trunk_v3.txt): 222.5 MB read + 234.2 MB written.  Algorithmic minimum: 67 MB
+                    # planes in + 24.8 MB weights + 1.6 MB head features out; the rest is write-back of the two 134 MB
+                    # activation buffers that L2 (126 MB) cannot hold entirely -- 1.4 % of the HBM peak, not a limiter
+                    "traffic": 456.7e6 if (G == 4096 and K == 1) else None, "traffic_unit": "bytes/launch",
                     "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 
     # ---- perft (secondary metric) and CPU baseline, rank 0 only ----
     perft = None
     cpu = None
+    kernels = None
     if rank == 0 and not args.no_perft:
         small = Engine(max_games=1, max_nodes=8)
         perft = perft_metric(small)
         small.close()
+        if not args.no_cpu_baseline and world == 1:
+            perft["cpu_baseline"] = cpu_perft_baseline()
+    if rank == 0 and not args.no_kernels:
+        kernels = kernel_rooflines(eng, peaks, flush, True)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s, t, ev, cores = cpu_reference_sims(20.0, 100)
         cpu = {"value": s / t, "unit": "simulations/s", "cores": cores, "kind": "port",
@@ -407,7 +537,7 @@ def main():
             "gpu_launches": int(launches_all),
             "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
             "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
-            "roofline": roof, "cpu_baseline": cpu, "perft": perft,
+            "roofline": roof, "cpu_baseline": cpu, "perft": perft, "kernels": kernels,
         }
         print(json.dumps(line))
     eng.close()

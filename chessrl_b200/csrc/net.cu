@@ -774,7 +774,8 @@ struct TrunkParams {
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
-k_trunk(const CUtensorMap* __restrict__ maps, const LayerDesc* __restrict__ layers, TrunkParams p) {
+k_trunk(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __restrict__ maps,
+        const LayerDesc* __restrict__ layers, TrunkParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -801,6 +802,7 @@ k_trunk(const CUtensorMap* __restrict__ maps, const LayerDesc* __restrict__ laye
   const int n_groups = (n_tiles + 1) >> 1;
   const int NL = p.n_layers;
 
+  if (threadIdx.x == 0) prefetch_tmap(&map_planes);
   if (threadIdx.x == 32) {
     for (int i = 0; i < V2_STAGES; ++i) {
       mbar_init(&full_bar[i], 2);
@@ -834,7 +836,7 @@ k_trunk(const CUtensorMap* __restrict__ maps, const LayerDesc* __restrict__ laye
     for (int grp = pair; grp < n_groups; grp += n_pairs) {
       for (int L = 0; L < NL; ++L, ++uses) {
         const LayerDesc ld = layers[L];
-        const CUtensorMap* map_a = maps + ld.map_in;
+        const CUtensorMap* map_a = ld.map_in == 0 ? &map_planes : maps + ld.map_in;   // planes: kernel parameter
         const CUtensorMap* map_w = maps + ld.map_w;
         const int n_kblocks = 9 * ld.k_chunks;
         for (int X = 0; X < 2; ++X) {
@@ -1104,10 +1106,9 @@ struct NetWeights {
   CUtensorMap map_pf, map_wp;
   // v3 (whole tower in one persistent kernel)
   bool use_trunk = true;
-  CUtensorMap* d_maps = nullptr;            // [3 + N_CONVS] device copies: planes, act[0], act[1], weights (128-filter boxes)
+  CUtensorMap* d_maps = nullptr;            // [3 + N_CONVS] device copies: (unused: the planes map is a kernel
+                                            // parameter), act[0], act[1], weights (128-filter boxes)
   LayerDesc* d_layers = nullptr;            // [N_CONVS]
-  const void* d_planes_map_for = nullptr;   // planes pointer / rows the device copy of map 0 was built for
-  int d_planes_map_rows = 0;
 };
 
 static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int cin, int rows) {
@@ -1483,13 +1484,6 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
   }
   int rc;
   if (nw->use_trunk) {
-    if (nw->d_planes_map_for != nw->planes_ptr || nw->d_planes_map_rows != nw->planes_rows) {
-      // stream-ordered update of map 0 (planes); the copy source must outlive the async copy -> keep it in NetWeights
-      CRL_CUDA(cudaMemcpyAsync(nw->d_maps, &nw->map_planes, sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
-      CRL_CUDA(cudaStreamSynchronize(e->stream));
-      nw->d_planes_map_for = nw->planes_ptr;
-      nw->d_planes_map_rows = nw->planes_rows;
-    }
     TrunkParams tp;
     tp.n_dev = n_dev;
     tp.n_host = n_host;
@@ -1503,7 +1497,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     if (pairs < 1) pairs = 1;
     {
       LaunchScope ls(e, KC_CONV);
-      k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->d_maps, nw->d_layers, tp);
+      k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
       CRL_CUDA(cudaGetLastError());
     }
     return launch_heads_v2(e, n_dev, n_host, policy, value);
