@@ -137,3 +137,78 @@ def test_agent_network_predictions_and_training_step(tmp_path):
     a2 = Agent(True, weights=path)
     assert all(np.array_equal(a, b) for a, b in zip(a2.model.weights, agent.model.weights))
     assert selfplay.get_model_path(str(tmp_path)).endswith("model-0.h5")
+
+
+def test_selfplaytree_threads_is_the_wave_schedule(golden_dir):
+    """SelfPlayTree(root, threads=K): the drop-in class runs the K-in-flight wave schedule (reference --threads K)."""
+    from chessrl_b200 import mctree
+    from chessrl_b200.agentdistributed import AgentDistributed
+    from chessrl_b200.game import Game
+    cases = [c for c in json.load(open(os.path.join(golden_dir, "mcts_wave.json")))["cases"]
+             if c["threads"] in (6, 32) and c["policy_bits"] == 24][:6]
+    assert cases
+    for c in cases:
+        g = Game(board=c["fen"]) if c["fen"] else Game()
+        for m in c["moves"]:
+            g.move(m)
+        agent = AgentDistributed(True, num_threads=c["threads"])
+        agent.use_hash_evaluator(c["eval_seed"], c["policy_bits"])
+        tree = mctree.SelfPlayTree(g, threads=c["threads"])
+        ret = tree.search_move(agent, max_iters=c["sims"], noise=False, ai_move=True)
+        assert list(ret) == c["returned"], (c["name"], c["threads"])
+        assert [k.visits for k in tree.root.children] == [k["visits"] for k in c["children"]]
+        assert [float(k.value) for k in tree.root.children] == [float.fromhex(k["value"]) for k in c["children"]]
+
+
+def test_gameagent_replies_with_policy_argmax():
+    """gameagent.GameAgent (gameagent.py:25-43): the agent answers every accepted move; bad agent -> ValueError."""
+    from chessrl_b200.agent import Agent
+    from chessrl_b200.gameagent import GameAgent
+    with pytest.raises(ValueError):
+        GameAgent(agent=3)
+    agent = Agent(False)                       # plays black
+    agent.use_hash_evaluator(3, 24)
+    oa = O.OAgent(O.hash_evaluator(3, 24))
+    ga = GameAgent(agent, player_color=True)
+    og = O.OGame()
+    assert ga.move("e2e5") is False and len(ga) == 0          # illegal: ignored, no reply
+    for mv in ("e2e4", "g1f3"):
+        assert ga.move(mv) is True
+        og.move(mv)
+        og.move(oa.best_move(og, real_game=True))
+        assert ga.get_history()["moves"] == [m.uci() for m in og.board.move_stack]
+    white = Agent(True)                        # agent plays white: it opens on the first move() call
+    white.use_hash_evaluator(3, 24)
+    gw = GameAgent(white, player_color=False)
+    assert gw.move("e7e5") is True and len(gw) == 1
+    assert gw.get_history()["moves"] == [oa.best_move(O.OGame(), real_game=True)]
+    cp = gw.get_copy()
+    assert isinstance(cp, GameAgent) and cp.agent is white and cp.get_history()["moves"] == gw.get_history()["moves"]
+
+
+def test_c_abi_argument_errors():
+    """Error behaviour of the boundary: negative status + crl_last_error text, never an exception from C."""
+    import ctypes
+    from chessrl_b200 import _lib
+    from chessrl_b200 import boards as B
+    from chessrl_b200.engine import Engine
+    lib = _lib.load()
+    h = _lib.vp()
+    assert lib.crl_create_ex(ctypes.byref(h), 0, 4, 16, 64, 0, None) == -1          # max_inflight < 1
+    assert lib.crl_create_ex(ctypes.byref(h), 0, 0, 16, 64, 1, None) == -1          # no lanes
+    assert b"bad arguments" in lib.crl_last_error()
+    e = Engine(max_games=2, max_nodes=8, max_inflight=2)
+    e.set_evaluator(_lib.EVAL_HASH, 1, 24)
+    with pytest.raises(_lib.CrlError):
+        e.mcts_simulate(4)                                                          # simulate before begin_move
+    e.games_set(np.tile(B.record_from_fen(), (2, 1)))
+    e.mcts_begin_move()
+    with pytest.raises(_lib.CrlError):
+        e.mcts_simulate(4, inflight=3)                                              # more than max_inflight
+    with pytest.raises(_lib.CrlError):
+        e.mcts_simulate(9)                                                          # more simulations than nodes
+    e.mcts_simulate(8, inflight=2)
+    assert (e.root_stats(want=("visits",))["root_visits"] == 9).all()
+    with pytest.raises(_lib.CrlError):
+        e.games_set(np.tile(B.record_from_fen(), (3, 1)))                            # more games than lanes
+    e.close()
