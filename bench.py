@@ -175,6 +175,42 @@ def perft_metric(engine):
     return out
 
 
+def perft_sharded(engine, rank, world, dist):
+    """perft over all ranks: the breadth-first frontier (>= 65,536 boards) is sharded board i -> rank i % world, every
+    rank walks its share, ONE all_reduce(sum) of a uint64 per root joins the counts.  Deeper roots
+    than the single-GPU variant so that every rank has work: start depth 6, Kiwipete depth 5."""
+    import torch
+    from chessrl_b200 import boards as B
+    out = {}
+    for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690)):
+        frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
+        d = 0
+        while frontier.shape[1] < 65536:
+            frontier, _ = engine.expand_frontier(frontier)
+            d += 1
+        mine = frontier[:, rank::world].contiguous()
+        best = None
+        for rep in range(4):
+            dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            nodes = engine.perft(mine, depth - d, bulk=True)
+            total = nodes.sum()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(total)                                         # int64 sum over ranks
+            assert int(total.item()) == want, (name, int(total.item()), want)
+            if rep > 0:
+                best = float(t.item()) if best is None else min(best, float(t.item()))
+        out[name] = {"nodes": want, "ms_max_over_ranks": best, "nodes_per_s": want / best * 1e3,
+                     "frontier_boards": int(frontier.shape[1]), "boards_per_rank": int(mine.shape[1]),
+                     "leaf_bulk_counting": True}
+    return out
+
+
 def _time_launch(fn, flush, reps=5):
     """Mean CUDA-event time (ms) of `fn` (one launch), L2 flushed before every timed launch, 3 warm-ups."""
     import torch
@@ -556,6 +592,11 @@ def main():
     perft = None
     cpu = None
     kernels = None
+    perft_multi = None
+    if world > 1 and not args.no_perft:
+        small = Engine(max_games=1, max_nodes=8)
+        perft_multi = perft_sharded(small, rank, world, dist)
+        small.close()
     if rank == 0 and not args.no_perft:
         small = Engine(max_games=1, max_nodes=8)
         perft = perft_metric(small)
@@ -590,7 +631,7 @@ def main():
             "gpu_launches": int(launches_all),
             "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
             "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
-            "roofline": roof, "cpu_baseline": cpu, "perft": perft, "kernels": kernels,
+            "roofline": roof, "cpu_baseline": cpu, "perft": perft, "perft_sharded": perft_multi, "kernels": kernels,
         }
         print(json.dumps(line))
     eng.close()
