@@ -181,6 +181,7 @@ def perft_sharded(engine, rank, world, dist):
     than the single-GPU variant so that every rank has work: start depth 6, Kiwipete depth 5."""
     import torch
     from chessrl_b200 import boards as B
+    from chessrl_b200 import sharding
     out = {}
     for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690)):
         frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
@@ -196,13 +197,12 @@ def perft_sharded(engine, rank, world, dist):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             nodes = engine.perft(mine, depth - d, bulk=True)
-            total = nodes.sum()
             b.record()
             torch.cuda.synchronize()
             t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dist.all_reduce(total)                                         # int64 sum over ranks
-            assert int(total.item()) == want, (name, int(total.item()), want)
+            total = sharding.sum_counts(nodes)                             # one all_reduce(sum) of an int64
+            assert total == want, (name, total, want)
             if rep > 0:
                 best = float(t.item()) if best is None else min(best, float(t.item()))
         out[name] = {"nodes": want, "ms_max_over_ranks": best, "nodes_per_s": want / best * 1e3,
@@ -212,13 +212,16 @@ def perft_sharded(engine, rank, world, dist):
 
 
 def _time_launch(fn, flush, reps=5):
-    """Mean CUDA-event time (ms) of `fn` (one launch), L2 flushed before every timed launch, 3 warm-ups."""
+    """Mean CUDA-event time (ms) of `fn` (one launch), L2 flushed before every timed launch, 3 warm-ups.
+    The flush writes a buffer larger than L2 and then READS it back, so the kernel under test does not also pay for
+    the write-back of the flush's dirty lines."""
     import torch
     for _ in range(3):
         fn()
     tot = 0.0
     for _ in range(reps):
         flush.fill_(1)
+        flush.max()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()

@@ -37,6 +37,14 @@ def shard_range(n_items, rank=None, world=None):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def sum_counts(counts):
+    """perft across ranks: every rank holds the node counts of ITS frontier boards (board i -> rank i % world);
+    one all_reduce(sum) of an int64 joins them.  Returns the total as a Python int on every rank."""
+    t = torch.as_tensor(counts).to(torch.int64).sum().reshape(1).to(_dev())
+    dist.all_reduce(t)
+    return int(t.item())
+
+
 def broadcast_weights(model, src=0):
     flat = torch.cat([torch.from_numpy(np.ascontiguousarray(w).reshape(-1)) for w in model.weights]).to(_dev())
     dist.broadcast(flat, src)

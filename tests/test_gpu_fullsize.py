@@ -1,6 +1,7 @@
 """GPU parity at BASELINE.json's FULL sizes (4,096 games x 200 simulations; 65,536 perft lanes) through
 size-independent properties, plus sampled lanes against the oracle.  The deterministic evaluator keeps the runs short
 and makes "identical network outputs" hold by construction."""
+import functools
 import random
 
 import numpy as np
@@ -15,6 +16,7 @@ pytestmark = pytest.mark.gpu
 G, S = 4096, 200
 
 
+@functools.lru_cache(maxsize=None)
 def _games(n, seed):
     """n seeded random openings (0-40 plies); every 8th lane repeats lane 0 so identical games sit far apart."""
     rng = random.Random(seed)

@@ -22,7 +22,9 @@ WORKER = textwrap.dedent("""
     words = [[(rank * 100 + g) * 1 + k for k in range(3 + g)] for g in range(2 + rank)]
     packed = sharding.pack_games(words, [1 if rank == 0 else None] * len(words), [bool(rank)] * len(words))
     got = sharding.gather_packed(*packed)
-    out = {"rank": rank, "range": [lo, hi], "same": bool(same)}
+    lanes = np.arange(1000, dtype=np.int64) ** 2 %% 977           # per-board node counts of a perft frontier
+    total = sharding.sum_counts(lanes[rank::world])               # board i -> rank i mod world, one all_reduce(sum)
+    out = {"rank": rank, "range": [lo, hi], "same": bool(same), "perft_total": total}
     if rank == 0:
         out["gathered"] = [[list(map(int, mv)), res, col] for mv, res, col in got]
     print("RESULT" + json.dumps(out))
@@ -46,6 +48,9 @@ def test_gloo_world2(tmp_path):
             res[r["rank"]] = r
     assert res[0]["range"] == [0, 6] and res[1]["range"] == [6, 11]
     assert res[0]["same"] and res[1]["same"]
+    import numpy as np
+    want = int((np.arange(1000, dtype=np.int64) ** 2 % 977).sum())
+    assert res[0]["perft_total"] == want and res[1]["perft_total"] == want
     g = res[0]["gathered"]
     assert len(g) == 2 + 3                                  # rank 0 sent 2 games, rank 1 sent 3, in rank order
     assert g[0][0] == [0, 1, 2] and g[1][0] == [1, 2, 3, 4]
