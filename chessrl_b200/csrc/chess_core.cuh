@@ -209,8 +209,10 @@ struct GenInfo {
 
 // Sink: void operator()(u16 move)   |  CountSink only counts (perft leaf bulk counting)
 struct StoreSink {
+  static constexpr bool kCounting = false;
   u16* out;
   int n;
+  CRL_HD void add(int) {}
   CRL_HD void put(u16 m) { out[n++] = m; }
   CRL_HD void put_set(int from, u64 targets) {   // MSB -> LSB
     while (targets) {
@@ -221,7 +223,9 @@ struct StoreSink {
   }
 };
 struct CountSink {
+  static constexpr bool kCounting = true;   // only the NUMBER of moves is wanted: pawn moves are counted set-wise
   int n;
+  CRL_HD void add(int k) { n += k; }
   CRL_HD void put(u16) { ++n; }
   CRL_HD void put_set(int, u64 targets) { n += popc64(targets); }
 };
@@ -240,28 +244,43 @@ CRL_HD bool ep_capture_safe(const Board& b, int from, int ep, int white, int ksq
   return true;
 }
 
-template <class Sink>
-CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
+// The generator is instantiated per side to move (WHITE is a compile-time constant): lockstep lanes move the same
+// colour at the same time, so the dispatch below does not diverge and every `white ? a : b` folds away.
+template <class Sink, int WHITE>
+CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   GenInfo info;
   info.in_check = 0;
   info.ep_legal = 0;
-  const int white = meta_turn(b.meta);
+  constexpr int white = WHITE;
   const u64 us = b.bb[white ? OCC_W : OCC_B], them = b.bb[white ? OCC_B : OCC_W];
   const u64 occ = us | them;
   const u64 kings = b.bb[KING] & us;
   if (!kings) return info;                         // never happens in legal chess
   const int ksq = msb64(kings);
   const u64 kbit = bit(ksq);
+  constexpr int base = white ? 0 : 56;
 
   const u64 checkers = attackers_of(b, ksq, occ, !white);
-  const u64 danger = attack_map(b, occ ^ kbit, !white);          // king may not step here
   info.in_check = checkers != 0;
 
-  // absolute pins (Board._slider_blockers)
+  // squares whose safety matters: the king's destinations and the castling paths that are otherwise clear.
+  // The enemy attack map (the most expensive part of the generator) is skipped when there are none -- a king
+  // boxed in by its own pieces, as in most opening positions.
+  const u64 king_targets = king_attacks_set(kbit) & ~us;
+  const int rights = meta_castle(b.meta) >> (white ? 0 : 2);
+  bool castle_k = false, castle_q = false;
+  if (!checkers && ksq == base + 4) {
+    castle_k = (rights & 1) && !(occ & (0x60ULL << base));
+    castle_q = (rights & 2) && !(occ & (0x0EULL << base));
+  }
+  u64 danger = 0;
+  if (king_targets || castle_k || castle_q) danger = attack_map(b, occ ^ kbit, !white);   // king may not step here
+
+  // absolute pins (Board._slider_blockers): enemy sliders on a line with the king (no occupancy needed for that)
   u64 pinned = 0;
   {
     u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & them, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & them;
-    u64 snipers = (rook_attacks(ksq, 0) & rq) | (bishop_attacks(ksq, 0) & bq);
+    u64 snipers = ((rank_mask(ksq) | file_mask(ksq)) & rq) | ((diag_mask(ksq) | anti_mask(ksq)) & bq);
     while (snipers) {
       int s = msb64(snipers);
       snipers ^= bit(s);
@@ -284,7 +303,7 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
       target = between(ksq, checker_sq) | checkers;
     }
     // python-chess emits king evasions first
-    sink.put_set(ksq, king_attacks_set(kbit) & ~us & ~danger);
+    sink.put_set(ksq, king_targets & ~danger);
     if (double_check) return info;
   }
 
@@ -297,7 +316,7 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
     officers ^= fb;
     u64 t;
     if (fb & b.bb[KNIGHT]) t = knight_attacks_set(fb);
-    else if (fb & b.bb[KING]) t = king_attacks_set(fb) & ~danger;
+    else if (fb & b.bb[KING]) t = king_targets & ~danger;
     else {
       t = 0;
       if (fb & (b.bb[BISHOP] | b.bb[QUEEN])) t = bishop_attacks(from, occ);
@@ -312,23 +331,30 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
   }
 
   // (2) castling (never while in check); king side first (rook candidates scanned h -> a)
-  if (!checkers) {
-    int rights = meta_castle(b.meta) >> (white ? 0 : 2);
-    int base = white ? 0 : 56;
-    if (ksq == base + 4) {
-      if ((rights & 1) && !(occ & (0x60ULL << base)) && !(danger & (0x60ULL << base)))
-        sink.put(mk_move(ksq, base + 6, 0));
-      if ((rights & 2) && !(occ & (0x0EULL << base)) && !(danger & (0x0CULL << base)))
-        sink.put(mk_move(ksq, base + 2, 0));
-    }
-  }
+  if (castle_k && !(danger & (0x60ULL << base))) sink.put(mk_move(ksq, base + 6, 0));
+  if (castle_q && !(danger & (0x0CULL << base))) sink.put(mk_move(ksq, base + 2, 0));
 
   const u64 pawns = b.bb[PAWN] & us;
   if (!pawns) return info;
-  const u64 promo_rank = white ? RANK_8 : RANK_1;
+  constexpr u64 promo_rank = white ? RANK_8 : RANK_1;
 
   // (3) pawn captures, source squares h8 -> a1, destinations high -> low, promotions Q R B N
-  {
+  if (Sink::kCounting) {
+    // counting only: unpinned pawns set-wise, pinned pawns (rare) one by one
+    const u64 free_p = pawns & ~pinned;
+    const u64 cl = white ? ((free_p << 7) & ~FILE_H) : ((free_p >> 9) & ~FILE_H);
+    const u64 cr = white ? ((free_p << 9) & ~FILE_A) : ((free_p >> 7) & ~FILE_A);
+    const u64 tl = cl & them & target, tr = cr & them & target;
+    sink.add(popc64(tl) + popc64(tr) + 3 * (popc64(tl & promo_rank) + popc64(tr & promo_rank)));
+    u64 src = pawns & pinned;
+    while (src) {
+      int from = msb64(src);
+      u64 fb = bit(from);
+      src ^= fb;
+      u64 t = pawn_attacks_set(fb, white) & them & target & line_through(ksq, from);
+      sink.add(popc64(t) + 3 * popc64(t & promo_rank));
+    }
+  } else {
     u64 src = pawns;
     while (src) {
       int from = msb64(src);
@@ -354,15 +380,13 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
   // (4) single pushes by destination, (5) double pushes by destination
   {
     u64 single, dbl;
-    int back;
+    constexpr int back = white ? -8 : 8;
     if (white) {
       single = (pawns << 8) & ~occ;
       dbl = (single << 8) & ~occ & (0xFFULL << 24);
-      back = -8;
     } else {
       single = (pawns >> 8) & ~occ;
       dbl = (single >> 8) & ~occ & (0xFFULL << 32);
-      back = 8;
     }
     single &= target;
     dbl &= target;
@@ -373,23 +397,27 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
       single &= white ? (ok_src << 8) : (ok_src >> 8);
       dbl &= white ? (ok_src << 16) : (ok_src >> 16);
     }
-    while (single) {
-      int to = msb64(single);
-      u64 tb = bit(to);
-      single ^= tb;
-      if (tb & promo_rank) {
-        sink.put(mk_move(to + back, to, QUEEN));
-        sink.put(mk_move(to + back, to, ROOK));
-        sink.put(mk_move(to + back, to, BISHOP));
-        sink.put(mk_move(to + back, to, KNIGHT));
-      } else {
-        sink.put(mk_move(to + back, to, 0));
+    if (Sink::kCounting) {
+      sink.add(popc64(single) + 3 * popc64(single & promo_rank) + popc64(dbl));
+    } else {
+      while (single) {
+        int to = msb64(single);
+        u64 tb = bit(to);
+        single ^= tb;
+        if (tb & promo_rank) {
+          sink.put(mk_move(to + back, to, QUEEN));
+          sink.put(mk_move(to + back, to, ROOK));
+          sink.put(mk_move(to + back, to, BISHOP));
+          sink.put(mk_move(to + back, to, KNIGHT));
+        } else {
+          sink.put(mk_move(to + back, to, 0));
+        }
       }
-    }
-    while (dbl) {
-      int to = msb64(dbl);
-      dbl ^= bit(to);
-      sink.put(mk_move(to + 2 * back, to, 0));
+      while (dbl) {
+        int to = msb64(dbl);
+        dbl ^= bit(to);
+        sink.put(mk_move(to + 2 * back, to, 0));
+      }
     }
   }
 
@@ -413,20 +441,28 @@ CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
   return info;
 }
 
+template <class Sink>
+CRL_HD GenInfo generate_legal(const Board& b, Sink& sink) {
+  return meta_turn(b.meta) ? generate_legal_side<Sink, 1>(b, sink) : generate_legal_side<Sink, 0>(b, sink);
+}
+
 // ---- make move (Board.push, standard chess) -------------------------------------------------------
+// No dynamically indexed access to b.bb[]: the record stays in registers (a runtime index would push it to
+// local memory).
 CRL_HD void make_move(Board& b, u16 mv) {
   const int from = mv_from(mv), to = mv_to(mv), promo = mv_promo(mv);
   const int white = meta_turn(b.meta);
-  const int us_i = white ? OCC_W : OCC_B, them_i = white ? OCC_B : OCC_W;
   const u64 fb = bit(from), tb = bit(to);
   int castle = meta_castle(b.meta);
   int half = meta_halfmove(b.meta) + 1, full = meta_fullmove(b.meta) + (white ? 0 : 1);
   const int ply = meta_ply(b.meta) + 1;
   const int old_ep = meta_ep(b.meta);
   int ep = -1;
+  u64 us = white ? b.bb[OCC_W] : b.bb[OCC_B];
+  u64 them = white ? b.bb[OCC_B] : b.bb[OCC_W];
 
   int pt = piece_at(b, from);
-  const bool capture = (b.bb[them_i] & tb) != 0;
+  const bool capture = (them & tb) != 0;
   const bool zeroing = pt == PAWN || capture;
   if (zeroing) half = 0;
 
@@ -437,28 +473,32 @@ CRL_HD void make_move(Board& b, u16 mv) {
                       ((own_rights & 1) && from == base + 7) || ((own_rights & 2) && from == base);
 
   // castling rights: any move from/to a rook home square kills that right; king move kills both
+  const u64 ft = fb | tb;
   int kill = 0;
-  if (fb & bit(7)) kill |= 1;
-  if (fb & bit(0)) kill |= 2;
-  if (fb & bit(63)) kill |= 4;
-  if (fb & bit(56)) kill |= 8;
-  if (tb & bit(7)) kill |= 1;
-  if (tb & bit(0)) kill |= 2;
-  if (tb & bit(63)) kill |= 4;
-  if (tb & bit(56)) kill |= 8;
+  if (ft & bit(7)) kill |= 1;
+  if (ft & bit(0)) kill |= 2;
+  if (ft & bit(63)) kill |= 4;
+  if (ft & bit(56)) kill |= 8;
   if (pt == KING) kill |= white ? 3 : 12;
   castle &= ~kill;
 
-  // lift the mover
-  b.bb[pt] ^= fb;
-  b.bb[us_i] ^= fb;
+  // a capture clears the target square everywhere first; then lift the mover
+  if (capture) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b.bb[k] &= ~tb;
+    them &= ~tb;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (k == pt) b.bb[k] ^= fb;
+  us ^= fb;
 
   if (pt == KING && (to - from == 2 || from - to == 2)) {
     // castling arrives as the king's two-square move; shift the rook as well
     int rook_from = to > from ? base + 7 : base;
     int rook_to = to > from ? base + 5 : base + 3;
     b.bb[ROOK] ^= bit(rook_from) | bit(rook_to);
-    b.bb[us_i] ^= bit(rook_from) | bit(rook_to);
+    us ^= bit(rook_from) | bit(rook_to);
   } else if (pt == PAWN) {
     int diff = to - from;
     if (diff == 16 || diff == -16) {
@@ -466,17 +506,16 @@ CRL_HD void make_move(Board& b, u16 mv) {
     } else if (to == old_ep && !capture && (diff == 7 || diff == 9 || diff == -7 || diff == -9)) {
       u64 vb = bit(to + (white ? -8 : 8));
       b.bb[PAWN] &= ~vb;
-      b.bb[them_i] &= ~vb;
+      them &= ~vb;
     }
   }
-  if (capture) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) b.bb[k] &= ~tb;
-    b.bb[them_i] &= ~tb;
-  }
   if (promo) pt = promo;
-  b.bb[pt] |= tb;
-  b.bb[us_i] |= tb;
+#pragma unroll
+  for (int k = 0; k < 6; ++k)
+    if (k == pt) b.bb[k] |= tb;
+  us |= tb;
+  b.bb[OCC_W] = white ? us : them;
+  b.bb[OCC_B] = white ? them : us;
 
   int rev = irreversible ? 0 : meta_revlen(b.meta) + 1;
   b.meta = meta_pack(!white, castle, ep, half, full, ply, rev);

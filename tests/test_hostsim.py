@@ -58,7 +58,9 @@ PERFT = [
 def test_device_core_perft(lib, fen, expected):
     rec = B.record_from_fen(fen)
     for d, e in enumerate(expected, 1):
-        assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 1) == e
+        assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 1) == e           # leaf bulk counting (CountSink: set-wise pawns)
+        if d <= 4:
+            assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 0) == e       # every leaf generated / made (StoreSink)
     assert lib.hs_perft(rec.ctypes.data_as(u64p), 3, 0) == expected[2]      # without leaf bulk counting
 
 
