@@ -467,7 +467,7 @@ def main():
     from chessrl_b200 import model
     from chessrl_b200._lib import EVAL_NET
     from chessrl_b200.engine import Engine
-    from chessrl_b200.lockstep import compute_policy
+    from chessrl_b200.lockstep import pick_moves
 
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -511,11 +511,7 @@ def main():
         eng.mcts_simulate(S, K)
         st = eng.root_stats(want=("visits",))                              # device -> host
         _, plies, results = eng.games_get(0, G)
-        picks = np.full(G, -1, dtype=np.int32)
-        for g in range(G):
-            k = int(st["n_children"][g])
-            if results[g] == B.RESULT_NONE and k:
-                picks[g] = int(np.argmax(compute_policy(st["visits"][g, :k], st["root_visits"][g], int(plies[g]), True)))
+        picks = pick_moves(st["visits"], st["n_children"], st["root_visits"], plies, results == B.RESULT_NONE, True)
         return eng.commit(picks, apply=False)                              # host -> device, device -> host
 
     np.random.seed(0)

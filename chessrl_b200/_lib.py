@@ -48,6 +48,8 @@ SIGNATURES = {
     "crl_perft": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "crl_expand_frontier": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int64, vp]),
     "crl_game_replay_host": (ctypes.c_int, [vp, c_u64p, c_u16p, ctypes.c_int, c_u16p, c_i32p, c_i8p, c_u8p, c_u64p]),
+    "crl_game_replay_records_host": (ctypes.c_int, [vp, c_u64p, c_u16p, ctypes.c_int, c_u16p, c_i32p, c_i8p, c_u8p,
+                                                    c_u64p, c_i32p]),
     "crl_encode": (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, vp]),
     "crl_policy_index": (ctypes.c_int, [vp, vp, vp, ctypes.c_int, vp]),
     "crl_label_table_host": (ctypes.c_int, [vp, c_i16p]),
@@ -58,6 +60,7 @@ SIGNATURES = {
     "crl_set_evaluator": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]),
     "crl_games_set_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u64p, c_u16p, c_i32p, ctypes.c_int]),
     "crl_games_get_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u64p, c_i32p, c_i8p]),
+    "crl_games_set_active_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u8p]),
     "crl_game_moves_host": (ctypes.c_int, [vp, ctypes.c_int, c_u16p, ctypes.c_int, c_i32p]),
     "crl_games_policy_move_host": (ctypes.c_int, [vp, c_u8p, c_u16p]),
     "crl_mcts_begin_move": (ctypes.c_int, [vp]),

@@ -363,18 +363,21 @@ int crl_expand_frontier(crl_engine* e, const uint64_t* boards_dev, int n, const 
   return launch_frontier(e, boards_dev, n, (const long long*)offsets_dev, out_dev, out_n, counts_dev);
 }
 
-int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
-                         uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host, uint8_t* accepted_host,
-                         uint64_t* final_host) {
+static int game_replay_impl(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
+                            uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host, uint8_t* accepted_host,
+                            uint64_t* final_host, uint64_t* records_host, int32_t* n_records_host) {
   CHECK_ENGINE(e);
   if (!start_host || n_moves < 0 || (n_moves > 0 && !moves_host)) {
     set_error("crl_game_replay_host: bad arguments");
     return CRL_EINVAL;
   }
-  // staging layout: [start 72 B][n_moves int][moves u16 x n][accepted u8 x n][legal u16 x 256][n_legal int]
+  const bool want_rec = records_host != nullptr;
+  // staging layout: [start 72 B][n_moves int][moves u16 x n][accepted u8 x n][legal u16 x 256][n_legal int][n_records int]
+  //                 [records 72 B x (n+1), only when asked for]
   size_t off_n = 72, off_mv = 80, off_acc = off_mv + ((size_t)n_moves * 2 + 7) / 8 * 8;
   size_t off_legal = off_acc + ((size_t)n_moves + 7) / 8 * 8, off_nl = off_legal + MAX_MOVES * 2;
-  size_t total = off_nl + 8;
+  size_t off_rec = off_nl + 8;
+  size_t total = off_rec + (want_rec ? ((size_t)n_moves + 1) * 72 : 0);
   int rc = ensure_stage(e, total);
   if (rc) return rc;
   char* h = (char*)e->h_stage;
@@ -383,8 +386,10 @@ int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16
   memcpy(h + off_n, &n_moves, 4);
   if (n_moves) memcpy(h + off_mv, moves_host, (size_t)n_moves * 2);
   CRL_CUDA(cudaMemcpyAsync(d, h, off_acc, cudaMemcpyHostToDevice, e->stream));
+  // the record stride of the kernel is (stride + 1) records per game: exactly n_moves + 1 here
   rc = launch_games_replay(e, 0, 1, (const u64*)d, (const u16*)(d + off_mv), (const int*)(d + off_n),
-                           n_moves > 0 ? n_moves : 1, (u8*)(d + off_acc));
+                           n_moves > 0 ? n_moves : 1, (u8*)(d + off_acc), want_rec ? (u64*)(d + off_rec) : nullptr,
+                           (int*)(d + off_nl + 4));
   if (rc) return rc;
   rc = launch_game_info(e, 0, 1, (u16*)(d + off_legal), (int*)(d + off_nl));
   if (rc) return rc;
@@ -401,7 +406,27 @@ int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16
   if (legal_host) memcpy(legal_host, h + off_legal, (size_t)nl * 2);
   if (result_host) *result_host = res;
   if (final_host) memcpy(final_host, rec, 72);
+  const int nrec = *(int*)(h + off_nl + 4);
+  if (n_records_host) *n_records_host = nrec;
+  if (want_rec) memcpy(records_host, h + off_rec, (size_t)nrec * 72);
   return check_pool_errors(e);
+}
+
+int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
+                         uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host, uint8_t* accepted_host,
+                         uint64_t* final_host) {
+  return game_replay_impl(e, start_host, moves_host, n_moves, legal_host, n_legal_host, result_host, accepted_host,
+                          final_host, nullptr, nullptr);
+}
+int crl_game_replay_records_host(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
+                                 uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host,
+                                 uint8_t* accepted_host, uint64_t* records_host, int32_t* n_records_host) {
+  if (!records_host || !n_records_host) {
+    set_error("crl_game_replay_records_host: null output");
+    return CRL_EINVAL;
+  }
+  return game_replay_impl(e, start_host, moves_host, n_moves, legal_host, n_legal_host, result_host, accepted_host,
+                          nullptr, records_host, n_records_host);
 }
 
 // ---- encoding ----------------------------------------------------------------------------------------
@@ -534,6 +559,22 @@ int crl_games_get_host(crl_engine* e, int first, int n, uint64_t* boards_host, i
     for (int i = 0; i < n; ++i)
       for (int k = 0; k < 9; ++k) boards_host[(size_t)i * 9 + k] = s[(size_t)k * n + i];
   }
+  return CRL_OK;
+}
+
+int crl_games_set_active_host(crl_engine* e, int first, int n, const uint8_t* active_host) {
+  CHECK_ENGINE(e);
+  if (first < 0 || n <= 0 || first + n > e->G || !active_host) {
+    set_error("crl_games_set_active_host: bad arguments (first %d, n %d, capacity %d)", first, n, e->G);
+    return CRL_EINVAL;
+  }
+  int rc = ensure_stage(e, (size_t)n);
+  if (rc) return rc;
+  u8* h = (u8*)e->h_stage;
+  for (int i = 0; i < n; ++i) h[i] = active_host[i] ? 1 : 0;
+  CRL_CUDA(cudaMemcpyAsync(e->P.g_active + first, h, (size_t)n, cudaMemcpyHostToDevice, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));   // the staging buffer is reused by the next call
+  e->tree_ready = false;
   return CRL_OK;
 }
 

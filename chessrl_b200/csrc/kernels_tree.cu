@@ -289,7 +289,8 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first,
                                                              const u64* __restrict__ start_aos,
                                                              const u16* __restrict__ moves,
                                                              const int* __restrict__ n_moves, int stride,
-                                                             u8* __restrict__ accepted) {
+                                                             u8* __restrict__ accepted, u64* __restrict__ records,
+                                                             int* __restrict__ n_records) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int g = first + i;
@@ -302,11 +303,18 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first,
   P.g_active[g] = 1;
   P.g_nnodes[g] = 0;
   game_refresh(P, g, nullptr, nullptr);
+  // optional: the record after every ACCEPTED move (AoS, record j of game i at records[(i*(stride+1) + j)*9]);
+  // record 0 is the start position.  This is what Board.copy() + pop() walks back through (netencoder.py:58-67).
+  int nrec = 0;
+  u64* rec = records ? records + (long long)i * (stride + 1) * 9 : nullptr;
+  if (rec) store_rec(rec + 9LL * nrec++, b);
   const int m = n_moves ? n_moves[i] : 0;
   for (int k = 0; k < m; ++k) {
     int ok = game_move(P, g, moves[(long long)i * stride + k]);
     if (accepted) accepted[(long long)i * stride + k] = (u8)ok;
+    if (rec && ok) store_rec(rec + 9LL * nrec++, load_soa(P.g_cur, P.G, g));
   }
+  if (n_records) n_records[i] = nrec;
 }
 
 // what game.Game exposes about the current position: legal moves (python-chess order) and get_result
@@ -358,10 +366,10 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __res
 
 // ---- launchers ----------------------------------------------------------------------------------------
 int launch_games_replay(crl_engine_impl* e, int first, int n, const u64* start_aos, const u16* moves,
-                        const int* n_moves, int stride, u8* accepted) {
+                        const int* n_moves, int stride, u8* accepted, u64* records, int* n_records) {
   LaunchScope ls(e, KC_GAME);
   k_games_replay<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, start_aos, moves, n_moves, stride,
-                                                                      accepted);
+                                                                      accepted, records, n_records);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

@@ -98,20 +98,34 @@ class Engine:
         check(self.lib.crl_expand_frontier(self.h, _ptr(boards_t), n, _ptr(offsets), _ptr(out), total, _ptr(counts)))
         return out, counts
 
-    def game_replay(self, start_record, moves):
-        """Game semantics for one game on slot 0: returns dict(legal, result, accepted, record)."""
+    def game_replay(self, start_record, moves, records=False):
+        """Game semantics for one game on slot 0: returns dict(legal, result, accepted, record[, records]).
+        records=True also returns the record after every accepted move ([n_accepted + 1, 9], records[0] = start)."""
         start = np.ascontiguousarray(np.asarray(start_record, dtype=np.uint64))
         mv = np.ascontiguousarray(np.asarray(moves, dtype=np.uint16))
         legal = np.zeros(B.MAX_MOVES, dtype=np.uint16)
         n_legal = ctypes.c_int32(0)
         result = ctypes.c_int8(0)
         accepted = np.zeros(max(len(mv), 1), dtype=np.uint8)
-        final = np.zeros(9, dtype=np.uint64)
-        check(self.lib.crl_game_replay_host(self.h, _np(start, ctypes.c_uint64), _np(mv, ctypes.c_uint16), len(mv),
-                                            _np(legal, ctypes.c_uint16), ctypes.byref(n_legal), ctypes.byref(result),
-                                            _np(accepted, ctypes.c_uint8), _np(final, ctypes.c_uint64)))
-        return {"legal": legal[:n_legal.value].copy(), "result": None if result.value == B.RESULT_NONE else int(result.value),
-                "accepted": accepted[:len(mv)].astype(bool), "record": final}
+        out = {}
+        if records:
+            recs = np.zeros((len(mv) + 1, 9), dtype=np.uint64)
+            n_rec = ctypes.c_int32(0)
+            check(self.lib.crl_game_replay_records_host(
+                self.h, _np(start, ctypes.c_uint64), _np(mv, ctypes.c_uint16), len(mv), _np(legal, ctypes.c_uint16),
+                ctypes.byref(n_legal), ctypes.byref(result), _np(accepted, ctypes.c_uint8), _np(recs, ctypes.c_uint64),
+                ctypes.byref(n_rec)))
+            out["records"] = recs[:n_rec.value].copy()
+            final = out["records"][-1].copy()
+        else:
+            final = np.zeros(9, dtype=np.uint64)
+            check(self.lib.crl_game_replay_host(self.h, _np(start, ctypes.c_uint64), _np(mv, ctypes.c_uint16), len(mv),
+                                                _np(legal, ctypes.c_uint16), ctypes.byref(n_legal), ctypes.byref(result),
+                                                _np(accepted, ctypes.c_uint8), _np(final, ctypes.c_uint64)))
+        out.update({"legal": legal[:n_legal.value].copy(),
+                    "result": None if result.value == B.RESULT_NONE else int(result.value),
+                    "accepted": accepted[:len(mv)].astype(bool), "record": final})
+        return out
 
     # ---- encoding -----------------------------------------------------------------------------------------
     def encode(self, boards_t, hist_t=None, hist_len_t=None):
@@ -203,6 +217,11 @@ class Engine:
         check(self.lib.crl_games_get_host(self.h, first, n, _np(rec, ctypes.c_uint64), _np(plies, ctypes.c_int32),
                                           _np(res, ctypes.c_int8)))
         return rec, plies, res
+
+    def games_set_active(self, active, first=0):
+        """Parks (0) / resumes (1) lanes first..first+len(active)-1; parked lanes are skipped by the search."""
+        a = np.ascontiguousarray(np.asarray(active, dtype=np.uint8))
+        check(self.lib.crl_games_set_active_host(self.h, int(first), len(a), _np(a, ctypes.c_uint8)))
 
     def game_moves(self, game):
         n = ctypes.c_int32(0)

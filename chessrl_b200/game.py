@@ -95,28 +95,28 @@ class Game(object):
 
     # ---- device round trip --------------------------------------------------------------------------------
     def _sync(self, extra=()):
-        """Replays moves (+ candidate moves) on the device; keeps the accepted ones."""
+        """Replays moves (+ candidate moves) on the device in ONE round trip; keeps the accepted ones."""
         eng = runtime.scalar_engine()
-        cand = list(self._moves) + list(extra)
+        extra = list(extra)
+        cand = list(self._moves) + extra
         words = [B.uci_to_move(m) for m in cand]
-        r = eng.game_replay(self._start, words)
         n_old = len(self._moves)
-        accepted_new = [m for m, ok in zip(cand[n_old:], r["accepted"][n_old:]) if ok]
-        if len(extra) > 1 and accepted_new:
-            # rebuild the per-ply records for a bulk load
-            self._moves = list(self._moves)
-            for m in accepted_new:
-                self._moves.append(m)
-                rr = eng.game_replay(self._start, [B.uci_to_move(x) for x in self._moves])
-                self._records.append(rr["record"].copy())
-            r = eng.game_replay(self._start, [B.uci_to_move(x) for x in self._moves])
-        elif accepted_new:
-            self._moves.append(accepted_new[0])
-            self._records.append(r["record"].copy())
+        if len(extra) > 1:
+            # bulk load: the kernel hands back the record after every accepted ply (crl_game_replay_records_host)
+            r = eng.game_replay(self._start, words, records=True)
+            self._moves = [m for m, ok in zip(cand, r["accepted"]) if ok]
+            self._records = [rec.copy() for rec in r["records"]]
+            played = len(self._moves) > n_old
+        else:
+            r = eng.game_replay(self._start, words)
+            played = bool(extra) and bool(r["accepted"][n_old])
+            if played:
+                self._moves.append(extra[0])
+                self._records.append(r["record"].copy())
         self._record = r["record"].copy()
         self._legal = [B.move_to_uci(m) for m in r["legal"]]
         self._result = r["result"]
-        return bool(accepted_new)
+        return played
 
     def _ep_legal(self):
         ep = B.meta_fields(self._record[8])["ep"]

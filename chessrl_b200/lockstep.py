@@ -34,6 +34,62 @@ def compute_policy(child_visits, root_visits, n_plies, noise=True):
     return policy
 
 
+_POW_CACHE = {}
+
+
+def _tempered(n_plies, count):
+    """np.power(count, 1 / tau) exactly as compute_policy evaluates it (same scalar call), memoised."""
+    key = (int(n_plies), int(count))
+    v = _POW_CACHE.get(key)
+    if v is None:
+        if len(_POW_CACHE) > (1 << 20):
+            _POW_CACHE.clear()
+        tau = key[0] / (1 + np.power(key[0], 1.3))
+        v = _POW_CACHE[key] = np.power(key[1], 1 / tau)
+    return v
+
+
+def pick_moves(child_visits, n_children, root_visits, n_plies, live, noise=True):
+    """argmax(compute_policy(...)) for every live game of a lockstep batch in one pass -> int32 picks (-1 = skip).
+
+    Bit-identical to calling compute_policy game by game in lane order, including the position of numpy's legacy
+    global RNG afterwards: np.random.dirichlet([a] * k) draws k standard gammas one after the other, sums them in
+    order and multiplies by the reciprocal, so one standard_gamma call for all live games, a per-row cumulative sum
+    and one multiply reproduce every draw (tests/test_host_policy.py checks this against the per-game calls).
+    """
+    child_visits = np.asarray(child_visits)
+    G = child_visits.shape[0]
+    picks = np.full(G, -1, dtype=np.int32)
+    k = np.where(np.asarray(live, dtype=bool), np.asarray(n_children, dtype=np.int64), 0)
+    rows = np.nonzero(k > 0)[0]
+    if rows.size == 0:
+        return picks
+    kr = k[rows]
+    kmax = int(kr.max())
+    mask = np.arange(kmax)[None, :] < kr[:, None]
+    vis = child_visits[rows, :kmax]
+    rv = np.asarray(root_visits)[rows]
+    pl = np.asarray(n_plies)[rows]
+    policy = np.zeros((rows.size, kmax), dtype=np.float64)
+    early = pl < 30
+    if early.any():                      # tau = 1
+        policy[early] = vis[early].astype(np.float64) / rv[early].astype(np.float64)[:, None]
+    for i in np.nonzero(~early)[0]:      # tau = n / (1 + n^1.3): the reference's scalar np.power calls, memoised
+        n = int(pl[i])
+        num = np.array([_tempered(n, v) for v in vis[i, :kr[i]]])
+        policy[i, :kr[i]] = num / _tempered(n, rv[i])
+    if noise:
+        g = np.random.standard_gamma(0.03, size=int(kr.sum()))
+        pad = np.zeros((rows.size, kmax), dtype=np.float64)
+        pad[mask] = g
+        inv = 1 / np.cumsum(pad, axis=1)[:, -1]
+        policy = (1 - 0.25) * policy + pad * inv[:, None]
+    policy[~mask] = -np.inf
+    # np.argmax returns the first maximum and the first NaN if there is one, row-wise as for the 1-D call
+    picks[rows] = np.argmax(policy, axis=1).astype(np.int32)
+    return picks
+
+
 class LockstepSelfPlay:
     """Plays `n_games` games in lockstep on one Engine.
 
@@ -54,6 +110,7 @@ class LockstepSelfPlay:
         self.finished = []          # (moves u16[], result, player_color)
         self.moves_played = 0
         self._harvested = np.zeros(self.n, dtype=bool)
+        self._retired = np.zeros(self.n, dtype=bool)
 
     def start(self, colors=None, start_records=None, move_lists=None):
         if colors is not None:
@@ -72,34 +129,61 @@ class LockstepSelfPlay:
         st = e.root_stats(want=("visits",))
         _, plies, results = e.games_get(0, self.n)
         picks = np.full(e.max_games, -1, dtype=np.int32)
-        for g in range(self.n):
-            k = int(st["n_children"][g])
-            if results[g] != B.RESULT_NONE or k == 0:
-                continue
-            pi = compute_policy(st["visits"][g, :k], st["root_visits"][g], int(plies[g]), self.noise)
-            picks[g] = int(np.argmax(pi))
+        picks[:self.n] = pick_moves(st["visits"][:self.n], st["n_children"][:self.n], st["root_visits"][:self.n], plies,
+                                    (results == B.RESULT_NONE) & ~self._retired, self.noise)
         out = e.commit(picks, apply=True)
         self.moves_played += int((picks >= 0).sum())
         return out[:self.n]
 
     def running(self):
         _, _, results = self.e.games_get(0, self.n)
-        return results == B.RESULT_NONE
+        return (results == B.RESULT_NONE) & ~self._retired
 
-    def harvest(self):
-        """Collects finished games (and restarts their lanes when refill=True)."""
-        rec, plies, results = self.e.games_get(0, self.n)
-        done = np.nonzero((results != B.RESULT_NONE) & ~self._harvested)[0]
+    def harvest(self, max_plies=None):
+        """Finished games since the last call: list of (lane, moves u16[], result, player_color); also kept in
+        self.finished as (moves, result, player_color).  max_plies: games that reached that many plies are
+        harvested unfinished (result None), like a capped play_game run.  With refill=True the lanes are restarted."""
+        _, plies, results = self.e.games_get(0, self.n)
+        over = results != B.RESULT_NONE
+        if max_plies is not None:
+            over = over | (plies >= max_plies)
+        done = np.nonzero(over & ~self._harvested & ~self._retired)[0]
+        out = []
         for g in done:
-            self.finished.append((self.e.game_moves(int(g)), int(results[g]), bool(self.colors[g])))
+            res = None if results[g] == B.RESULT_NONE else int(results[g])
+            out.append((int(g), self.e.game_moves(int(g)), res, bool(self.colors[g])))
             self._harvested[g] = True
+        self.finished.extend((m, r, c) for _, m, r, c in out)
         if self.refill and len(done):
-            start = B.record_from_fen()
-            mask = np.zeros(self.e.max_games, dtype=np.uint8)
-            for g in done:
-                self.e.games_set(start[None, :], None, first=int(g))
-                self._harvested[g] = False
-                mask[g] = 0 if self.colors[g] else 1
-            if mask.any():
-                self.e.policy_move(mask=mask)
-        return len(done)
+            self.restart(done, [self.colors[g] for g in done])
+        return out
+
+    def restart(self, lanes, colors):
+        """Per-GPU slot refill: a new game from the start position in every listed lane; where the
+        agent plays black the opponent opens with its policy-argmax move (selfplay.py:68-70)."""
+        lanes = [int(g) for g in lanes]
+        if not lanes:
+            return
+        start = B.record_from_fen()
+        mask = np.zeros(self.e.max_games, dtype=np.uint8)
+        # contiguous runs of lanes go down in one call each
+        run0 = 0
+        order = sorted(range(len(lanes)), key=lambda i: lanes[i])
+        srt = [lanes[i] for i in order]
+        for i in range(1, len(srt) + 1):
+            if i == len(srt) or srt[i] != srt[i - 1] + 1:
+                self.e.games_set(np.tile(start, (i - run0, 1)), None, first=srt[run0])
+                run0 = i
+        for i, g in enumerate(lanes):
+            self.colors[g] = bool(colors[i])
+            self._harvested[g] = False
+            self._retired[g] = False
+            mask[g] = 0 if self.colors[g] else 1
+        if mask.any():
+            self.e.policy_move(mask=mask)
+
+    def retire(self, lanes):
+        """Lanes that stay empty from now on (no game left to start): step() skips them."""
+        for g in lanes:
+            self._retired[int(g)] = True
+            self.e.games_set_active([0], first=int(g))

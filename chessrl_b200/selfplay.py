@@ -56,34 +56,64 @@ def play_game(agent, max_iters=900):
 
 
 def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
-                        threads=1):
-    """`n_games` games in lockstep; returns a DatasetGame.  The per-move host work is the numpy move policy only."""
-    from ._lib import EVAL_NET
+                        threads=1, evaluator=None, stats=None):
+    """`n_games` games in lockstep, `lanes` at a time; returns a DatasetGame in game-start order.
+
+    A lane whose game ends is refilled with the next game at once (per-GPU slot refill), so the
+    evaluation batches stay full until fewer than `lanes` games remain.  The per-move host work is the numpy move
+    policy only.  max_moves caps the agent moves of a game (it is then stored unfinished, result None).
+    evaluator: None = the network with `model`'s weights; ("hash", seed, bits) = the deterministic test evaluator.
+    stats: optional dict that receives steps / moves / simulations / seconds of the run."""
+    import time
+    from ._lib import EVAL_HASH, EVAL_NET
     from .engine import Engine
     from .lockstep import LockstepSelfPlay
-    lanes = n_games if lanes is None else min(lanes, n_games)
+    lanes = n_games if lanes is None else max(1, min(lanes, n_games))
     threads = max(1, min(int(threads), 64))
     eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads)
-    eng.load_weights(model.weights)
-    eng.set_evaluator(EVAL_NET)
+    if evaluator is None:
+        eng.load_weights(model.weights)
+        eng.set_evaluator(EVAL_NET)
+    else:
+        eng.set_evaluator(EVAL_HASH, int(evaluator[1]), int(evaluator[2]))
     rng = random.Random(seed)
-    out = DatasetGame()
-    remaining = n_games
-    while remaining > 0:
-        n = min(lanes, remaining)
-        sp = LockstepSelfPlay(eng, n_games=n, sims=sims, noise=noise, inflight=threads)
-        colors = [rng.random() >= 0.5 for _ in range(n)]
-        sp.start(colors=colors)
-        moves = 0
-        while sp.running().any() and (max_moves is None or moves < max_moves):
-            sp.step()
-            moves += 1
-        for g in range(n):
-            gm = Game(player_color=colors[g])
-            gm._sync(extra=[B.move_to_uci(m) for m in eng.game_moves(g)])
-            out.append(gm)
-        remaining -= n
+    colors = [rng.random() >= 0.5 for _ in range(n_games)]       # colour of game i, drawn like selfplay.py:62
+    sp = LockstepSelfPlay(eng, n_games=lanes, sims=sims, noise=noise, inflight=threads)
+    t0 = time.perf_counter()
+    c0 = eng.counters()
+    sp.start(colors=colors[:lanes])
+    lane_game = list(range(lanes))                               # which game runs in which lane
+    next_game = lanes
+    records = [None] * n_games
+    cap = None if max_moves is None else 2 * max_moves
+    steps = 0
+    while True:
+        again, parked = [], []
+        for lane, moves, result, color in sp.harvest(max_plies=cap):
+            records[lane_game[lane]] = (moves, color)
+            if next_game < n_games:
+                lane_game[lane] = next_game
+                again.append(lane)
+                next_game += 1
+            else:
+                parked.append(lane)
+        sp.restart(again, [colors[lane_game[g]] for g in again])   # one batch: games_set per run + one opening eval
+        sp.retire(parked)
+        if not sp.running().any():
+            break
+        sp.step()
+        steps += 1
+    if stats is not None:
+        c1 = eng.counters()
+        stats.update({"steps": steps, "moves": sp.moves_played, "seconds": time.perf_counter() - t0,
+                      "simulations": c1["simulations"] - c0["simulations"],
+                      "evaluations": c1["evaluations"] - c0["evaluations"], "lanes": lanes})
     eng.close()
+    out = DatasetGame()
+    for moves, color in records:
+        gm = Game(player_color=color)
+        gm._sync(extra=[B.move_to_uci(m) for m in moves])
+        out.append(gm)
     return out
 
 

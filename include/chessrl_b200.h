@@ -93,6 +93,14 @@ int crl_game_replay_host(crl_engine* e, const uint64_t* start_host, const uint16
                          uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host,
                          uint8_t* accepted_host, uint64_t* final_host);
 
+/* the same replay, additionally returning the record after EVERY accepted move (records_host [(n_moves+1)][9],
+ * record 0 = start position; *n_records_host = accepted moves + 1): the positions Board.copy() + pop() walks back
+ * through for the history planes (netencoder.py:58-67) and DatasetGame.augment_game replays ply by ply
+ * (dataset.py:21-43) -- one device round trip per game instead of one per ply. */
+int crl_game_replay_records_host(crl_engine* e, const uint64_t* start_host, const uint16_t* moves_host, int n_moves,
+                                 uint16_t* legal_host, int32_t* n_legal_host, int8_t* result_host,
+                                 uint8_t* accepted_host, uint64_t* records_host, int32_t* n_records_host);
+
 /* ---- encoding: netencoder ------------------------------------------------------------------------- */
 /* netencoder.get_game_state (netencoder.py:72-91).  hist_dev: bitboards of the previous positions,
  * word k of the i-th previous position of board b at hist_dev[((i*8)+k)*n + b], i = 0..7 (may be NULL);
@@ -130,6 +138,10 @@ int crl_games_set_host(crl_engine* e, int first, int n, const uint64_t* start_ho
 /* per game: current record (AoS), plies played, Game.get_result (CRL_RESULT_NONE = running). NULLs allowed */
 int crl_games_get_host(crl_engine* e, int first, int n, uint64_t* boards_host, int32_t* plies_host,
                        int8_t* results_host);
+/* lanes first..first+n-1: active_host[i] == 0 parks the lane (no search, no moves; its record stays readable),
+ * != 0 resumes it.  crl_games_set_host activates the lanes it loads.  Used by the lockstep driver when no game is
+ * left to start in a lane (per-GPU slot refill, the many-games form of selfplay.py:147-159's game loop). */
+int crl_games_set_active_host(crl_engine* e, int first, int n, const uint8_t* active_host);
 /* the moves of one game so far (DatasetGame / Game.get_history 'moves') */
 int crl_game_moves_host(crl_engine* e, int game, uint16_t* moves_host, int cap, int32_t* n_host);
 /* AgentDistributed.best_move(real_game=True) (agentdistributed.py:56-58): policy argmax over legal moves for

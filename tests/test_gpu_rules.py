@@ -149,6 +149,32 @@ def test_game_replay_semantics(engine1):
     assert engine1.game_replay(start, cyc * 4)["result"] == 0
 
 
+def test_game_replay_records_one_round_trip(engine1):
+    """crl_game_replay_records_host: the record after every ACCEPTED ply equals replaying the prefixes one by one,
+    and the drop-in Game builds its history from it (bulk load = one device round trip)."""
+    from chessrl_b200.game import Game
+    start = B.record_from_fen()
+    ucis = ["e2e4", "e7e5", "e2e5", "g1f3", "00000", "b8c6", "f1b5", "a7a6", "b5c6", "d7c6", "e1g1"]
+    words = [B.uci_to_move(m) for m in ucis]
+    r = engine1.game_replay(start, words, records=True)
+    kept = [m for m, ok in zip(ucis, r["accepted"]) if ok]
+    assert kept == [m for m in ucis if m not in ("e2e5", "00000")]
+    assert r["records"].shape == (len(kept) + 1, 9) and (r["records"][0] == start).all()
+    for j in range(len(kept) + 1):
+        one = engine1.game_replay(start, [B.uci_to_move(m) for m in kept[:j]])
+        assert (one["record"] == r["records"][j]).all(), j
+    assert (r["record"] == r["records"][-1]).all()
+    empty = engine1.game_replay(start, [], records=True)
+    assert empty["records"].shape == (1, 9) and (empty["records"][0] == start).all()
+    g = Game()
+    g._sync(extra=ucis)
+    og = O.OGame()
+    for m in kept:
+        og.move(m)
+    assert g.board.move_stack == kept and g.get_legal_moves() == og.get_legal_moves()
+    assert [tuple(x) for x in g.history_records()] == [tuple(x) for x in r["records"][::-1][:9]]
+
+
 def test_game_results_along_golden_games(engine1, golden_dir):
     cases = [c for c in json.load(open(os.path.join(golden_dir, "rules.json")))["cases"] if not c["fen"]]
     for c in cases:

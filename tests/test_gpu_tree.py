@@ -179,6 +179,25 @@ def test_selfplay_golden_with_noise(golden_dir):
         e.close()
 
 
+def test_selfplay_slot_refill_plays_the_same_games():
+    """play_games_lockstep with fewer lanes than games (finished lanes are refilled at once, parked at the end) returns,
+    game for game, what one lane per game returns; parked lanes do no work."""
+    from chessrl_b200 import selfplay
+    kw = dict(sims=12, noise=False, seed=3, max_moves=70, evaluator=("hash", 9, 24))
+    s_wide, s_narrow = {}, {}
+    wide = selfplay.play_games_lockstep(None, 10, lanes=10, stats=s_wide, **kw)
+    narrow = selfplay.play_games_lockstep(None, 10, lanes=3, stats=s_narrow, **kw)
+    assert len(wide) == len(narrow) == 10
+    for a, b in zip(wide.games, narrow.games):
+        assert a.get_history()["moves"] == b.get_history()["moves"] and a.player_color == b.player_color
+        assert a.get_result() == b.get_result()
+        assert len(a) > 0
+    assert {g.player_color for g in wide.games} == {True, False}                 # both openings are exercised
+    assert s_narrow["moves"] == s_wide["moves"]                                  # the same agent moves were searched
+    assert s_narrow["simulations"] == s_wide["simulations"]                      # parked / finished lanes did none
+    assert s_narrow["steps"] > s_wide["steps"]
+
+
 def test_lockstep_lanes_are_independent():
     """The same game in 64 lanes (plus different games in between) gives identical trees: no cross-lane state."""
     from chessrl_b200.engine import Engine
