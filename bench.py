@@ -172,18 +172,43 @@ def perft_metric(engine):
         total_nodes += want
         total_ms += best
     out["nodes_per_s"] = total_nodes / total_ms * 1e3
+    # sustained throughput: two plies deeper from the same kind of frontier (depth 5 is over in about a millisecond,
+    # which mostly measures launch latency).  Totals are the published perft values.
+    for name, fen, depth, want in (("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
+        frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
+        d = 0
+        while frontier.shape[1] < 65536:
+            frontier, _ = engine.expand_frontier(frontier)
+            d += 1
+        res = {"nodes": want, "lanes": int(frontier.shape[1]), "plies_per_lane": depth - d}
+        for bulk in (True, False):
+            best = None
+            for rep in range(2):
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                nodes = engine.perft(frontier, depth - d, bulk=bulk)
+                b.record()
+                torch.cuda.synchronize()
+                assert int(nodes.sum().item()) == want, (name, int(nodes.sum().item()), want)
+                ms = a.elapsed_time(b)
+                best = ms if best is None else min(best, ms)
+            res["ms_%s" % ("bulk" if bulk else "no_bulk")] = round(best, 3)
+            res["nodes_per_s_%s" % ("bulk" if bulk else "no_bulk")] = want / best * 1e3
+        out[name] = res
     return out
 
 
 def perft_sharded(engine, rank, world, dist):
     """perft over all ranks: the breadth-first frontier (>= 65,536 boards) is sharded board i -> rank i % world, every
     rank walks its share, ONE all_reduce(sum) of a uint64 per root joins the counts.  Deeper roots
-    than the single-GPU variant so that every rank has work: start depth 6, Kiwipete depth 5."""
+    than the single-GPU variant so that every rank has work: start depth 6 / 7, Kiwipete depth 5 / 6."""
     import torch
     from chessrl_b200 import boards as B
     from chessrl_b200 import sharding
     out = {}
-    for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690)):
+    for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690),
+                                   ("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
         frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
         d = 0
         while frontier.shape[1] < 65536:
@@ -437,7 +462,14 @@ def run_reference(args, rank, world):
 
 
 def WORKLOAD(args):
-    return "lockstep self-play %d games/GPU x %d sims/move, random-init ChessRL net (BASELINE configs[3])" % (args.games, args.sims)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.games * world == 65536 and args.sims == 800:
+        which = "BASELINE configs[4]: 65,536 games x 800 sims/move sharded by game over %d GPU(s)" % world
+    elif args.games == 4096 and args.sims == 200:
+        which = "BASELINE configs[3] per GPU"
+    else:
+        which = "a scaled variant of BASELINE configs[3]"
+    return "lockstep self-play %d games/GPU x %d sims/move, random-init ChessRL net (%s)" % (args.games, args.sims, which)
 
 
 def main():
@@ -564,7 +596,7 @@ def main():
         eng.profile(True)
         c0 = eng.counters()
         eng.mcts_begin_move()
-        eng.mcts_simulate(min(S, 16 * K), K)
+        eng.mcts_simulate(min(S, 200 * K), K)      # a whole step (capped at 200 waves), so clocks are the sustained ones
         torch.cuda.synchronize()
         prof = eng.profile_read()
         c1 = eng.counters()

@@ -140,7 +140,7 @@ int crl_games_get_host(crl_engine* e, int first, int n, uint64_t* boards_host, i
                        int8_t* results_host);
 /* lanes first..first+n-1: active_host[i] == 0 parks the lane (no search, no moves; its record stays readable),
  * != 0 resumes it.  crl_games_set_host activates the lanes it loads.  Used by the lockstep driver when no game is
- * left to start in a lane (per-GPU slot refill, the many-games form of selfplay.py:147-159's game loop). */
+ * left to start in a lane (per-GPU slot refill, the many-games form of selfplay.py:142-162's game loop). */
 int crl_games_set_active_host(crl_engine* e, int first, int n, const uint8_t* active_host);
 /* the moves of one game so far (DatasetGame / Game.get_history 'moves') */
 int crl_game_moves_host(crl_engine* e, int game, uint16_t* moves_host, int cap, int32_t* n_host);
