@@ -607,16 +607,19 @@ def main():
             flop_per_launch = evals * CONV_FLOP_PER_POS / conv["launches"]
             t_launch = conv["ms"] * 1e-3 / conv["launches"]
             achieved = flop_per_launch / t_launch / 1e12
-            roof = {"bound": "tensor", "kernel": "k_trunk (the 21 tcgen05 cta_group::2 implicit-GEMM 3x3 convolutions of the residual "
-                    "tower as ONE persistent CTA-pair kernel)", "achieved": achieved,
+            v3 = os.environ.get("CRL_TRUNK_V3") == "1"
+            roof = {"bound": "tensor", "kernel": ("k_trunk (v3)" if v3 else "k_trunk4") + " (the 21 tcgen05 cta_group::2 implicit-GEMM "
+                    "3x3 convolutions of the residual tower as ONE persistent CTA-pair kernel" +
+                    ("" if v3 else "; the zero-padded board image of each 64-channel slice is loaded once and serves all nine filter taps "
+                     "through shifted shared-memory descriptors") + ")", "achieved": achieved,
                     "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_tflops_sustained"],
                     "peak_source": peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6,
                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4,096 positions, mean of 2 captured
-                    # launches (profiles/r01_ncu_trunk_v3.txt): 222.5 MB read + 234.2 MB written.  Algorithmic minimum: 67 MB
+                    # launches (profiles/r01_ncu_trunk_v4.txt): 219.6 MB read + 234.1 MB written.  Algorithmic minimum: 67 MB
                     # planes in + 24.8 MB weights + 1.6 MB head features out; the rest is write-back of the two 134 MB
                     # activation buffers that L2 (126 MB) cannot hold entirely -- 1.4 % of the HBM peak, not a limiter
-                    "traffic": 456.7e6 if (G == 4096 and K == 1) else None, "traffic_unit": "bytes/launch",
+                    "traffic": (456.7e6 if v3 else 453.7e6) if (G == 4096 and K == 1) else None, "traffic_unit": "bytes/launch",
                     "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 
     # ---- perft (secondary metric) and CPU baseline, rank 0 only ----

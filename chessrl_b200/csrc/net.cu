@@ -990,6 +990,270 @@ k_trunk(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __res
   }
 }
 
+// ======================================================================================================
+// v4: the tower kernel with the im2col operand REUSED across the nine filter taps.
+// v3 fetches one 16 KB A tile per (tap, 64-channel slice): the same activations cross L2 -> shared memory nine times.
+// Here the TMA unit loads, once per 64-channel slice, the zero-padded IMAGE of the CTA's two boards
+//     rows [y = -1..8][board 0..1][x = -1..8] x 64 channels  (200 rows of 128 bytes, 128-byte swizzle)
+// through a tensor map whose dimensions are ordered (C, W, B, H), so that out-of-board rows / columns are zero-filled
+// by the TMA unit exactly as before.  The A operand of tap (dy, dx) is then the SAME image addressed through a
+// shifted shared-memory descriptor: start row (1+dy)*20 + (1+dx), 8-row groups 1,280 bytes apart (one image row of
+// ten pixels), group g = 2*y + board.  Rows of a tile are therefore ordered (y, board, x) instead of (board, y, x);
+// the epilogue un-permutes when it computes its global row.  Per (tile, layer) a CTA now reads 4 x 25.6 KB of
+// activations instead of 36 x 16 KB; the weight stream (36 x 16 KB) is unchanged and gets its own, deeper ring.
+// ======================================================================================================
+static constexpr int T4_NA = 3;                           // padded-image slots
+static constexpr int T4_NB = 7;                           // weight stages
+static constexpr int T4_IMG_ROWS = 200;                   // 10 x 2 x 10
+static constexpr int T4_IMG_BYTES = T4_IMG_ROWS * 128;    // 25,600
+static constexpr int T4_A_SLOT = 26 * 1024;               // slot pitch (1,024-byte aligned)
+static constexpr int T4_B_BYTES = 128 * BLOCK_K * 2;      // 16 KB: this CTA's half of the 256 filters
+static constexpr int T4_SMEM_BYTES = 1024 + T4_NA * T4_A_SLOT + T4_NB * T4_B_BYTES + 2 * TILE_N * 4 + 3 * 256 * 4 + 64 + 512;
+
+// K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __restrict__ maps,
+         const LayerDesc* __restrict__ layers, TrunkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + T4_NA * T4_A_SLOT;
+  float* s_scale = (float*)(smem_b + T4_NB * T4_B_BYTES);
+  float* s_shift = s_scale + TILE_N;
+  float* s_hw = s_shift + TILE_N;
+  float* s_hs = s_hw + 3 * 256;
+  uint64_t* bars = (uint64_t*)(s_hs + 16);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + T4_NA;
+  uint64_t* b_full = a_empty + T4_NA;
+  uint64_t* b_empty = b_full + T4_NB;
+  uint64_t* tmem_full = b_empty + T4_NB;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint64_t* act_ready = tmem_empty + 2;
+  uint32_t* tmem_slot = (uint32_t*)(act_ready + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  int n_boards = p.n_host;
+  if (p.n_dev) n_boards = min(n_boards, *p.n_dev);
+  const int n_tiles = (n_boards + 3) >> 2;          // 256-row tiles (4 boards)
+  const int n_groups = (n_tiles + 1) >> 1;
+  const int NL = p.n_layers;
+
+  if (threadIdx.x == 0) prefetch_tmap(&map_planes);
+  if (threadIdx.x == 32) {
+    for (int i = 0; i < T4_NA; ++i) {
+      mbar_init(&a_full[i], 2);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < T4_NB; ++i) {
+      mbar_init(&b_full[i], 2);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 256);
+      mbar_init(&act_ready[i], 128);
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 3 * 256; i += CONV_THREADS) s_hw[i] = p.head_w[i];
+  if (threadIdx.x < 6) s_hs[threadIdx.x] = p.head_s[threadIdx.x];
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    // ================= TMA producer =================
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int uses = 0;
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const LayerDesc ld = layers[L];
+        const CUtensorMap* map_a = ld.map_in == 0 ? &map_planes : maps + ld.map_in;
+        const CUtensorMap* map_w = maps + ld.map_w;
+        for (int X = 0; X < 2; ++X) {
+          const int tile = 2 * grp + X;
+          if (L > 0) mbar_wait(&act_ready[X], (uint32_t)((uses - 1) & 1));
+          for (int kc = 0; kc < ld.k_chunks; ++kc) {
+            mbar_wait(&a_empty[as], aphase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[as], 2 * T4_IMG_BYTES);
+            // coordinates (channel, x, board, y): the box {64, 10, 2, 10} starts one pixel outside the board
+            tma2_load_4d(smem_a + as * T4_A_SLOT, map_a, &a_full[as], kc * BLOCK_K, -1, tile * 4 + (int)rank * 2, -1);
+            if (rank != 0) mbar_arrive_remote(&a_full[as], 0);
+            if (++as == T4_NA) {
+              as = 0;
+              aphase ^= 1;
+            }
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_empty[bs], bphase ^ 1);
+              if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * T4_B_BYTES);
+              tma2_load_2d(smem_b + bs * T4_B_BYTES, map_w, &b_full[bs], (tap * ld.k_chunks + kc) * BLOCK_K, (int)rank * 128);
+              if (rank != 0) mbar_arrive_remote(&b_full[bs], 0);
+              if (++bs == T4_NB) {
+                bs = 0;
+                bphase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (threadIdx.x == 32 && rank == 0) {
+    // ================= MMA issuer (leader CTA) =================
+    int as = 0, bs = 0;
+    uint32_t aphase = 0, bphase = 0;
+    int uses = 0;
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const int k_chunks = layers[L].k_chunks;
+        for (int X = 0; X < 2; ++X) {
+          mbar_wait(&tmem_empty[X], (uint32_t)((uses & 1) ^ 1));
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + X * TILE_N;
+          for (int kc = 0; kc < k_chunks; ++kc) {
+            mbar_wait(&a_full[as], aphase);
+            const uint32_t img = smem_u32(smem_a + as * T4_A_SLOT);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&b_full[bs], bphase);
+              tcgen05_fence_after();
+              const int dy = tap / 3, dx = tap - 3 * dy;                 // already offset by +1
+              const uint64_t da = make_kmajor_sw128_desc_sbo(img + (uint32_t)(dy * 20 + dx) * 128u, 1280u);
+              const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + bs * T4_B_BYTES));
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC, (kc | tap | k) != 0);
+              umma2_commit_both(&b_empty[bs]);
+              if (++bs == T4_NB) {
+                bs = 0;
+                bphase ^= 1;
+              }
+            }
+            umma2_commit_both(&a_empty[as]);
+            if (kc == k_chunks - 1) umma2_commit_both(&tmem_full[X]);
+            if (++as == T4_NA) {
+              as = 0;
+              aphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    if (uses > 0) {
+      mbar_wait(&tmem_empty[0], (uint32_t)((uses - 1) & 1));
+      mbar_wait(&tmem_empty[1], (uint32_t)((uses - 1) & 1));
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs) =================
+    const int q = warp & 3;
+    const int m = q * 32 + lane;                       // accumulator row = (y, board, x): g = m / 8 = 2*y + board
+    const int eb = (m >> 3) & 1, ey = m >> 4, ex = m & 7;
+    int uses = 0;
+    for (int grp = pair; grp < n_groups; grp += n_pairs) {
+      for (int L = 0; L < NL; ++L, ++uses) {
+        const LayerDesc ld = layers[L];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = threadIdx.x - 128; i < TILE_N; i += 128) {
+          s_scale[i] = ld.scale[i];
+          s_shift[i] = ld.shift[i];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int X = 0; X < 2; ++X) {
+          const int tile = 2 * grp + X;
+          mbar_wait(&tmem_full[X], (uint32_t)(uses & 1));
+          tcgen05_fence_after();
+          const int board = tile * 4 + (int)rank * 2 + eb;
+          const long long grow = (long long)board * 64 + ey * 8 + ex;
+          const bool valid = board < n_boards;
+          __nv_bfloat16* orow = ld.write_out ? ld.out + grow * TILE_N : nullptr;
+          const __nv_bfloat16* rrow = ld.residual ? ld.residual + grow * TILE_N : nullptr;
+          float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < TILE_N; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + X * TILE_N + c0, v);
+            tmem_ld_wait();
+            if (!valid) continue;
+            uint4 res[4];
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) res[j] = *reinterpret_cast<const uint4*>(rrow + c0 + 8 * j);
+            }
+            float a[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) a[j] = __uint_as_float(v[j]) * s_scale[c0 + j] + s_shift[c0 + j];
+            if (rrow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t* rj = reinterpret_cast<const uint32_t*>(&res[j]);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  a[8 * j + 2 * h] += __uint_as_float(rj[h] << 16);
+                  a[8 * j + 2 * h + 1] += __uint_as_float(rj[h] & 0xFFFF0000u);
+                }
+              }
+            }
+            if (ld.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.f);
+            }
+            if (ld.fuse_heads) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float x = __bfloat162float(__float2bfloat16_rn(a[j]));
+                h0 = fmaf(x, s_hw[c0 + j], h0);
+                h1 = fmaf(x, s_hw[256 + c0 + j], h1);
+                h2 = fmaf(x, s_hw[512 + c0 + j], h2);
+              }
+            }
+            if (orow) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  __nv_bfloat162 b2 = __floats2bfloat162_rn(a[8 * j + 2 * h], a[8 * j + 2 * h + 1]);
+                  pk[h] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          tcgen05_fence_before();
+          mbar_arrive_remote(&tmem_empty[X], 0);
+          if (ld.fuse_heads && valid) {
+            const float f0 = fmaxf(h0 * s_hs[0] + s_hs[3], 0.f), f1 = fmaxf(h1 * s_hs[1] + s_hs[4], 0.f);
+            reinterpret_cast<__nv_bfloat162*>(p.pf_out)[grow] = __floats2bfloat162_rn(f0, f1);
+            p.vf_out[grow] = fmaxf(h2 * s_hs[2] + s_hs[5], 0.f);
+          }
+          __threadfence();
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+          mbar_arrive(&act_ready[X]);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // softmax over the policy logits + the value head's two dense layers; 8 positions per block, one warp each
 struct TailParams {
   const int* n_rows_dev;
@@ -1104,6 +1368,11 @@ struct NetWeights {
   float* bp_pad = nullptr;                  // [2048]
   float* ones = nullptr;                    // [2048]
   CUtensorMap map_pf, map_wp;
+  // v4 (tower kernel with the padded-image A operand reused across the nine taps)
+  bool use_trunk4 = true;
+  CUtensorMap map_act4[2];
+  CUtensorMap map_planes4;
+  CUtensorMap* d_maps4 = nullptr;
   // v3 (whole tower in one persistent kernel)
   bool use_trunk = true;
   CUtensorMap* d_maps = nullptr;            // [3 + N_CONVS] device copies: (unused: the planes map is a kernel
@@ -1121,6 +1390,22 @@ static int make_act_map(NetWeights* nw, CUtensorMap* map, const void* base, int 
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activations) failed: %d", (int)r);
+    return CRL_ECUDA;
+  }
+  return CRL_OK;
+}
+// v4: the same activations seen as (C, W, B, H), box {64, 10, 2, 10} = the zero-padded image of two boards laid out
+// [y][board][x] in shared memory (see k_trunk4)
+static int make_act_map4(NetWeights* nw, CUtensorMap* map, const void* base, int cin, int rows) {
+  cuuint64_t dims[4] = {(cuuint64_t)cin, 8, (cuuint64_t)rows, 8};
+  cuuint64_t strides[3] = {(cuuint64_t)cin * 2, (cuuint64_t)cin * 128, (cuuint64_t)cin * 16};
+  cuuint32_t box[4] = {BLOCK_K, 10, 2, 10};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = nw->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activations, padded image) failed: %d", (int)r);
     return CRL_ECUDA;
   }
   return CRL_OK;
@@ -1194,6 +1479,7 @@ int net_create(crl_engine_impl* e) {
     if ((rc = dev_alloc(e, &nw->act[i], (size_t)nw->cap_rows * 64 * 256))) return rc;
     CRL_CUDA(cudaMemsetAsync(nw->act[i], 0, (size_t)nw->cap_rows * 64 * 256 * 2, e->stream));
     if ((rc = make_act_map(nw, &nw->map_act[i], nw->act[i], 256, nw->cap_rows))) return rc;
+    if ((rc = make_act_map4(nw, &nw->map_act4[i], nw->act[i], 256, nw->cap_rows))) return rc;
   }
   if ((rc = dev_alloc(e, &nw->w1x1, 3 * 256))) return rc;
   if ((rc = dev_alloc(e, &nw->s1x1, 6))) return rc;
@@ -1207,6 +1493,7 @@ int net_create(crl_engine_impl* e) {
   CRL_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_conv_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
   {
     // tensor-map table + layer table for the whole-tower kernel
     const char* nt = getenv("CRL_NO_TRUNK");
@@ -1219,6 +1506,14 @@ int net_create(crl_engine_impl* e) {
     hm[2] = nw->map_act[1];
     for (int i = 0; i < N_CONVS; ++i) hm[3 + i] = nw->map_w2[i];
     CRL_CUDA(cudaMemcpyAsync(nw->d_maps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
+    const char* t3 = getenv("CRL_TRUNK_V3");
+    nw->use_trunk4 = nw->use_trunk && !(t3 && t3[0] == '1');
+    if ((rc = dev_alloc(e, &nw->d_maps4, 3 + N_CONVS))) return rc;
+    std::vector<CUtensorMap> hm4(hm);
+    hm4[1] = nw->map_act4[0];
+    hm4[2] = nw->map_act4[1];
+    CRL_CUDA(cudaMemcpyAsync(nw->d_maps4, hm4.data(), hm4.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
+    CRL_CUDA(cudaStreamSynchronize(e->stream));   // hm4 is a local
     std::vector<LayerDesc> hl(N_CONVS);
     for (int L = 0; L < N_CONVS; ++L) {
       LayerDesc& d = hl[L];
@@ -1478,6 +1773,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     if (planes != nw->planes_ptr || rows != nw->planes_rows) {
       int rc = make_act_map(nw, &nw->map_planes, planes, 128, rows);
       if (rc) return rc;
+      if ((rc = make_act_map4(nw, &nw->map_planes4, planes, 128, rows))) return rc;
       nw->planes_ptr = planes;
       nw->planes_rows = rows;
     }
@@ -1497,7 +1793,10 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     if (pairs < 1) pairs = 1;
     {
       LaunchScope ls(e, KC_CONV);
-      k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
+      if (nw->use_trunk4)
+        k_trunk4<<<2 * pairs, CONV_THREADS, T4_SMEM_BYTES, e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp);
+      else
+        k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
       CRL_CUDA(cudaGetLastError());
     }
     return launch_heads_v2(e, n_dev, n_host, policy, value);
