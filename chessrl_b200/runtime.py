@@ -17,7 +17,7 @@ def scalar_engine(min_nodes=1024, min_inflight=1):
         if _scalar is not None:
             nodes, inflight = max(nodes, _scalar.max_nodes), max(inflight, _scalar.max_inflight)
             _scalar.close()
-        _scalar = Engine(max_games=1, max_nodes=nodes, avg_moves=96, max_inflight=inflight)
+        _scalar = Engine(max_games=1, max_nodes=nodes, avg_moves=218, max_inflight=inflight)   # 218 = most legal moves of any position
         _loaded_token = None
     return _scalar
 

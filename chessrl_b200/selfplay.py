@@ -55,6 +55,18 @@ def play_game(agent, max_iters=900):
     return gam
 
 
+def edge_slots_per_node(lanes, nodes, device=None, bytes_per_edge=24, share=0.5):
+    """Edge-pool sizing for long runs: every tree node reserves one edge slot per legal move of its position, and no
+    chess position has more than 218 legal moves, so 218 slots per node can never overflow.  That is what a run gets
+    whenever it fits in `share` of the free device memory (4,096 lanes x 901 nodes: 19 GB of a B200's 180 GB);
+    otherwise as many as fit (an overflow is then reported as CRL_ENOMEM, never silent)."""
+    import torch
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        free, _ = torch.cuda.mem_get_info()
+    fit = int(share * free / max(1, lanes * nodes * bytes_per_edge))
+    return max(48, min(218, fit))
+
+
 def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
                         threads=1, evaluator=None, stats=None):
     """`n_games` games in lockstep, `lanes` at a time; returns a DatasetGame in game-start order.
@@ -70,7 +82,8 @@ def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device
     from .lockstep import LockstepSelfPlay
     lanes = n_games if lanes is None else max(1, min(lanes, n_games))
     threads = max(1, min(int(threads), 64))
-    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads)
+    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads,
+                 avg_moves=edge_slots_per_node(lanes, sims + 1, device))
     if evaluator is None:
         eng.load_weights(model.weights)
         eng.set_evaluator(EVAL_NET)
@@ -126,6 +139,7 @@ def main(argv=None):
     parser.add_argument('--debug', action='store_true', default=False, help="Log debug messages on screen. Default false.")
     parser.add_argument('--sims', type=int, default=900, help="MCTS simulations per move (reference: 900)")
     parser.add_argument('--lanes', type=int, default=None, help="games stepped in lockstep per GPU")
+    parser.add_argument('--max-moves', type=int, default=None, help="cap on the agent's moves per game (stored unfinished)")
     parser.add_argument('--no-train', action='store_true', default=False)
     args = parser.parse_args(argv)
 
@@ -146,8 +160,14 @@ def main(argv=None):
         sharding.broadcast_weights(agent.model)
     share = args.games // world + (1 if rank < args.games % world else 0)
     logger.info("rank %d/%d plays %d game(s), %d simulations per move" % (rank, world, share, args.sims))
+    stats = {}
     data = (play_games_lockstep(agent.model, share, sims=args.sims, lanes=args.lanes, device=local_rank,
-                                threads=args.threads) if share else DatasetGame())
+                                threads=args.threads, max_moves=args.max_moves, stats=stats) if share else DatasetGame())
+    if stats:
+        full = max(1, stats["steps"] * stats["lanes"] * args.sims)
+        logger.info("rank %d: %d games, %d agent moves in %d lockstep steps, %.1f s: %.0f simulations/s, lane occupancy %.1f %%"
+                    % (rank, len(data), stats["moves"], stats["steps"], stats["seconds"],
+                       stats["simulations"] / max(stats["seconds"], 1e-9), 100.0 * stats["simulations"] / full))
     if world > 1:
         from . import sharding
         data = sharding.gather_games(data)

@@ -127,3 +127,30 @@ def test_search_with_network_evaluator_runs_and_counts(net_engine):
     # all 32 lanes hold the same position and the same weights -> identical trees
     assert (st["visits"] == st["visits"][0]).all()
     e2.close()
+
+
+@pytest.mark.parametrize("n", [1, 5, 37, 1000])
+def test_tower_v4_operand_reuse_matches_v3_and_fp32(n, monkeypatch):
+    """k_trunk4 (padded board image loaded once per channel slice, nine taps through shifted shared-memory
+    descriptors, rows ordered (y, board, x)) against the v3 tower (one TMA box per tap) and the fp32 graph:
+    odd batch sizes exercise the partial tile / zero-filled board rows; policy <= 2e-3, value <= 2e-2 vs fp32."""
+    from chessrl_b200.engine import Engine
+    pack = model.random_pack(seed=5, perturb_bn=True)
+    torch.manual_seed(n)
+    planes = (torch.rand(n, 8, 8, 128, device="cuda") < 0.2).to(torch.bfloat16)
+    planes[..., 127] = 0
+    out = {}
+    for v3 in ("1", "0"):
+        monkeypatch.setenv("CRL_TRUNK_V3", v3)
+        e = Engine(max_games=max(n, 2), max_nodes=4)
+        e.load_weights(pack)
+        p, v = e.net_forward(planes)
+        out[v3] = (p.cpu(), v.cpu())
+        e.close()
+    rp, rv = model_torch.forward(pack, planes[..., :127].float().cpu().numpy(), device="cuda")
+    rp, rv = rp.cpu(), rv.cpu().reshape(-1)
+    for key in ("1", "0"):
+        assert (out[key][0] - rp).abs().max().item() <= 2e-3, key
+        assert (out[key][1] - rv).abs().max().item() <= 2e-2, key
+    assert (out["1"][0] - out["0"][0]).abs().max().item() <= 2e-3
+    assert (out["1"][1] - out["0"][1]).abs().max().item() <= 4e-2
