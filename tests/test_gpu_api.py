@@ -212,3 +212,28 @@ def test_c_abi_argument_errors():
     with pytest.raises(_lib.CrlError):
         e.games_set(np.tile(B.record_from_fen(), (3, 1)))                            # more games than lanes
     e.close()
+
+
+def test_cli_selfplay_then_supervised(tmp_path):
+    """The two entry points end to end (selfplay.py:111-167, supervised.py:66-95): lockstep games with slot refill ->
+    gameplays.json in the reference's format -> training -> weights saved in place; then supervised training on that file."""
+    from chessrl_b200 import selfplay, supervised
+    from chessrl_b200.agent import Agent
+    from chessrl_b200.dataset import DatasetGame
+    d = str(tmp_path)
+    selfplay.main([d, "--games", "6", "--lanes", "3", "--sims", "8", "--max-moves", "4"])
+    items = json.load(open(os.path.join(d, "gameplays.json")))
+    assert len(items) == 6
+    for it in items:
+        assert set(it) == {"moves", "result", "player_color", "date"} and 7 <= len(it["moves"]) <= 9
+        assert it["result"] in (None, 1, 0, -1) and isinstance(it["player_color"], bool)
+    path = selfplay.get_model_path(d)
+    assert os.path.exists(path)
+    w0 = [w.copy() for w in Agent(True, weights=path).model.weights]
+    selfplay.main([d, "--games", "2", "--sims", "4", "--max-moves", "2", "--no-train"])      # appends (dataset.py:60-71)
+    ds = DatasetGame()
+    ds.load(os.path.join(d, "gameplays.json"))
+    assert len(ds) == 8
+    supervised.main([d, os.path.join(d, "gameplays.json"), "--epochs", "1", "--bs", "2"])
+    w1 = Agent(True, weights=path).model.weights
+    assert any(not np.array_equal(a, b) for a, b in zip(w0, w1))
