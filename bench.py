@@ -122,39 +122,40 @@ def synthetic_games(engine, n_games, seed):
 
 
 def perft_metric(engine):
-    """perft depth 5 from start + Kiwipete: BFS to >= 65,536 boards, then lockstep DFS per lane."""
+    """perft of the start position and Kiwipete (published totals, bit-exact):
+      depth 5 over >= 65,536 lockstep boards (BASELINE configs[1]) and two plies deeper over >= 1 Mi boards, each as ONE
+      crl_perft_root_host call (device-side breadth-first plies with atomic placement, then a depth-first walk per lane;
+      no host round trip in between), timed with CUDA events around the call, with and without leaf bulk counting;
+      plus the replicated variant: 65,536 copies of the root, every lane runs perft(3) in lockstep."""
     import torch
     from chessrl_b200 import boards as B
     out = {}
-    total_nodes, total_ms = 0, 0.0
-    for name, fen, want in (("start", B.STARTING_FEN, 4865609), ("kiwipete", KIWI, 193690690)):
-        best = None
-        for rep in range(3):
+
+    def timed_root(fen, depth, want, bulk, min_frontier, reps=3):
+        rec = B.record_from_fen(fen)
+        best, info = None, None
+        for rep in range(reps + 1):                     # the first call sizes the engine's frontier buffers
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
             a.record()
-            frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
-            depth = 0
-            while frontier.shape[1] < 65536:
-                frontier, _ = engine.expand_frontier(frontier)
-                depth += 1
-            nodes = engine.perft(frontier, 5 - depth, bulk=True)
-            total = int(nodes.sum().item())
+            total, lanes, plies = engine.perft_root(rec, depth, bulk=bulk, min_frontier=min_frontier)
             b.record()
             torch.cuda.synchronize()
-            ms = a.elapsed_time(b)
-            assert total == want, (name, total, want)
-            best = ms if best is None else min(best, ms)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        nodes_nb = engine.perft(frontier, 5 - depth, bulk=False)
-        b.record()
-        torch.cuda.synchronize()
-        assert int(nodes_nb.sum().item()) == want
-        out[name] = {"nodes": want, "ms": round(best, 3), "nodes_per_s": want / best * 1e3, "lanes": int(frontier.shape[1]),
-                     "leaf_bulk_counting": True, "headline": "with leaf bulk counting, frontier expansion included",
-                     "dfs_only_no_bulk_nodes_per_s": want / a.elapsed_time(b) * 1e3}
+            assert total == want, (fen, depth, total, want)
+            if rep:
+                ms = a.elapsed_time(b)
+                best = ms if best is None else min(best, ms)
+            info = (lanes, plies)
+        return best, info
+
+    total_nodes, total_ms = 0, 0.0
+    for name, fen, want in (("start", B.STARTING_FEN, 4865609), ("kiwipete", KIWI, 193690690)):
+        ms, (lanes, plies) = timed_root(fen, 5, want, True, 65536)
+        ms_nb, _ = timed_root(fen, 5, want, False, 65536)
+        out[name] = {"nodes": want, "depth": 5, "ms": round(ms, 4), "nodes_per_s": want / ms * 1e3, "lanes": lanes,
+                     "breadth_first_plies": plies, "leaf_bulk_counting": True,
+                     "headline": "one crl_perft_root_host call: device-side frontier expansion + per-lane walk, leaf bulk counting",
+                     "no_bulk_ms": round(ms_nb, 4), "no_bulk_nodes_per_s": want / ms_nb * 1e3}
         # replicated variant (SURVEY.md 8(d) config 2): 65,536 copies of the root, every lane runs perft(3) in lockstep
         rep = engine.boards_to_device(np.tile(B.record_from_fen(fen), (65536, 1)))
         per_lane = {"start": 8902, "kiwipete": 97862}[name]
@@ -170,37 +171,22 @@ def perft_metric(engine):
             out[name]["replicated_65536_lanes_perft3_%s_nodes_per_s" % ("bulk" if bulk else "no_bulk")] = \
                 65536 * per_lane / a.elapsed_time(b) * 1e3
         total_nodes += want
-        total_ms += best
+        total_ms += ms
     out["nodes_per_s"] = total_nodes / total_ms * 1e3
-    # sustained throughput: two plies deeper (depth 5 is over in about a millisecond, which mostly measures launch
-    # latency).  The breadth-first frontier is grown to >= 1 Mi boards (start: 4,865,609 at depth 5, Kiwipete: 4,085,603
-    # at depth 4) so that every lane walks only two plies: sibling lanes then do nearly the same amount of work and
-    # warps stay converged -- 2.2-2.5x the throughput of 65,536-board frontiers with three plies per lane
-    # (scripts/perft_frontier_probe.py).  Frontier expansion is inside the timed region.  Totals are the published values.
+    # sustained throughput: two plies deeper (depth 5 is over in a fraction of a millisecond).  The breadth-first
+    # frontier is grown to >= 1 Mi boards (start: 4,865,609 at depth 5, Kiwipete: 4,085,603 at depth 4) so that every lane
+    # walks only two plies: sibling lanes then do nearly the same amount of work and warps stay converged -- 2.2-2.5x the
+    # throughput of 65,536-board frontiers with three plies per lane (scripts/perft_frontier_probe.py).
+    deep_nodes, deep_ms = 0, 0.0
     for name, fen, depth, want in (("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
-        res = {"nodes": want}
-        for bulk in (True, False):
-            best = None
-            for rep in range(2):
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                torch.cuda.synchronize()
-                a.record()
-                frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
-                d = 0
-                while frontier.shape[1] < (1 << 20) and d < depth - 1:
-                    frontier, _ = engine.expand_frontier(frontier)
-                    d += 1
-                nodes = engine.perft(frontier, depth - d, bulk=bulk)
-                b.record()
-                torch.cuda.synchronize()
-                assert int(nodes.sum().item()) == want, (name, int(nodes.sum().item()), want)
-                ms = a.elapsed_time(b)
-                best = ms if best is None else min(best, ms)
-            res["lanes"], res["plies_per_lane"] = int(frontier.shape[1]), depth - d
-            res["ms_%s" % ("bulk" if bulk else "no_bulk")] = round(best, 3)
-            res["nodes_per_s_%s" % ("bulk" if bulk else "no_bulk")] = want / best * 1e3
-            del frontier, nodes
-        out[name] = res
+        ms, (lanes, plies) = timed_root(fen, depth, want, True, 1 << 20, reps=2)
+        ms_nb, _ = timed_root(fen, depth, want, False, 1 << 20, reps=1)
+        out[name] = {"nodes": want, "depth": depth, "lanes": lanes, "breadth_first_plies": plies, "plies_per_lane": depth - plies,
+                     "ms_bulk": round(ms, 3), "nodes_per_s_bulk": want / ms * 1e3,
+                     "ms_no_bulk": round(ms_nb, 3), "nodes_per_s_no_bulk": want / ms_nb * 1e3}
+        deep_nodes += want
+        deep_ms += ms
+    out["deep_nodes_per_s"] = deep_nodes / deep_ms * 1e3
     return out
 
 

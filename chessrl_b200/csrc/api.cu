@@ -313,6 +313,11 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
 }
 
 int crl_destroy(crl_engine* e) {
+  if (e) {
+    for (int i = 0; i < 2; ++i)
+      if (e->perft_buf[i]) cudaFree(e->perft_buf[i]);
+    e->perft_buf[0] = e->perft_buf[1] = nullptr;
+  }
   if (!e) return CRL_OK;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
@@ -352,6 +357,55 @@ int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int b
     return CRL_EINVAL;
   }
   return launch_perft(e, boards_dev, n, depth, bulk, (unsigned long long*)nodes_dev);
+}
+int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier,
+                        uint64_t* total_host, int64_t* lanes_host, int32_t* bfs_plies_host) {
+  CHECK_ENGINE(e);
+  if (!root_host || !total_host || depth < 0 || min_frontier < 1) {
+    set_error("crl_perft_root_host: bad arguments");
+    return CRL_EINVAL;
+  }
+  if (!e->perft_ctl) {
+    CRL_CUDA(cudaMalloc((void**)&e->perft_ctl, 8 * sizeof(unsigned long long)));
+    e->allocs.push_back(e->perft_ctl);
+  }
+  // capacity: the frontier stops growing once it holds min_frontier boards, so 16x leaves room for one more ply of a
+  // quiet position; a bushier frontier overflows, which is detected on the device and retried with four times the room
+  long long cap = min_frontier * 16;
+  if (cap < (1 << 16)) cap = 1 << 16;
+  for (int attempt = 0; attempt < 4; ++attempt, cap *= 4) {
+    if (cap > e->perft_cap) {
+      for (int i = 0; i < 2; ++i) {
+        if (e->perft_buf[i]) cudaFree(e->perft_buf[i]);
+        e->perft_buf[i] = nullptr;
+      }
+      e->perft_cap = 0;
+      for (int i = 0; i < 2; ++i) {
+        cudaError_t err = cudaMalloc((void**)&e->perft_buf[i], (size_t)cap * 72);
+        if (err != cudaSuccess) {
+          set_error("crl_perft_root_host: cudaMalloc(%lld boards) failed: %s", cap, cudaGetErrorString(err));
+          return CRL_ENOMEM;
+        }
+      }
+      e->perft_cap = cap;
+    }
+    const long long stride = e->perft_cap;
+    // the root record goes to column 0 of buffer 0 (structure of arrays: word k at [k * stride])
+    CRL_CUDA(cudaMemcpy2DAsync(e->perft_buf[0], (size_t)stride * 8, root_host, 8, 8, 9, cudaMemcpyHostToDevice, e->stream));
+    int rc = launch_perft_root(e, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk, min_frontier);
+    if (rc) return rc;
+    unsigned long long ctl[8];
+    CRL_CUDA(cudaMemcpyAsync(ctl, e->perft_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e->stream));
+    CRL_CUDA(cudaStreamSynchronize(e->stream));
+    if (ctl[3] == 0) {
+      *total_host = depth == 0 ? 1 : ctl[4];
+      if (lanes_host) *lanes_host = (int64_t)ctl[0];
+      if (bfs_plies_host) *bfs_plies_host = (int32_t)ctl[2];
+      return CRL_OK;
+    }
+  }
+  set_error("crl_perft_root_host: the breadth-first frontier does not fit (min_frontier %lld)", (long long)min_frontier);
+  return CRL_ENOMEM;
 }
 int crl_expand_frontier(crl_engine* e, const uint64_t* boards_dev, int n, const int64_t* offsets_dev, uint64_t* out_dev,
                         int64_t out_n, int32_t* counts_dev) {

@@ -50,6 +50,10 @@ struct crl_engine_impl {
   int* d_n = nullptr;                    // [2] their row counts
   u16* d_tmp_moves = nullptr;            // [2*G] scratch for picks
   int* d_tmp_pick = nullptr;             // [G]
+  // device-driven perft (crl_perft_root_host): two frontier buffers of perft_cap boards + control block
+  u64* perft_buf[2] = {nullptr, nullptr};
+  long long perft_cap = 0;
+  unsigned long long* perft_ctl = nullptr;
   // pinned staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
@@ -109,6 +113,8 @@ int launch_make(crl_engine_impl* e, u64* boards, int n, const u16* moves);
 int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bulk, unsigned long long* nodes);
 int launch_frontier(crl_engine_impl* e, const u64* boards, int n, const long long* offsets, u64* out,
                     long long out_n, int* counts);
+int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl, int depth, int bulk,
+                      long long min_frontier);
 int launch_encode_boards(crl_engine_impl* e, const u64* boards, const u64* hist, const u8* hist_len, int n,
                          __nv_bfloat16* planes);
 int launch_policy_index(crl_engine_impl* e, const u16* moves, const int* counts, int n, int16_t* idx);

@@ -88,21 +88,14 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_make(u64* __restrict__ boards, 
 // ---- perft: depth-first per lane with an explicit stack ----------------------------------------------
 static constexpr int PERFT_MAX_DEPTH = 8;
 
-// (80 registers, 6 blocks per SM; forcing 64 registers / 8 blocks measured 3-7 % slower on B200)
-__global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ boards, int n, int depth, int bulk,
-                                                       unsigned long long* __restrict__ nodes) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (depth <= 0) {
-    nodes[i] = 1;
-    return;
-  }
+// one lane: depth-first walk below `root` with an explicit stack (depth >= 1)
+__device__ __forceinline__ unsigned long long perft_lane(const Board& root, int depth, int bulk) {
   Board stack_b[PERFT_MAX_DEPTH];
   u16 stack_m[PERFT_MAX_DEPTH][MAX_MOVES];
   int stack_n[PERFT_MAX_DEPTH], stack_i[PERFT_MAX_DEPTH];
   unsigned long long total = 0;
   int level = 0;   // level L holds a position at distance L from the root; remaining plies = depth - L
-  stack_b[0] = load_soa(boards, n, i);
+  stack_b[0] = root;
   stack_n[0] = -1;
   while (level >= 0) {
     const int remaining = depth - level;
@@ -140,7 +133,97 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ b
     stack_n[level + 1] = -1;
     ++level;
   }
-  nodes[i] = total;
+  return total;
+}
+
+// (80 registers, 6 blocks per SM; forcing 64 registers / 8 blocks measured 3-7 % slower on B200)
+__global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ boards, int n, int depth, int bulk,
+                                                       unsigned long long* __restrict__ nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (depth <= 0) {
+    nodes[i] = 1;
+    return;
+  }
+  nodes[i] = perft_lane(load_soa(boards, n, i), depth, bulk);
+}
+
+// ---- perft of ONE root without host round trips -----------------------------------------------------------
+// Breadth-first plies (children placed with one warp-aggregated atomicAdd per warp, so their order is arbitrary --
+// a perft total does not care) until the frontier holds >= min_frontier boards, then one depth-first walk per lane.
+// Whether a ply still expands is decided on the device from the control block, so the host enqueues the whole
+// sequence blindly: no count pass, no prefix sum, no synchronisation between plies.
+//   ctl[0] boards in the current frontier   ctl[1] boards placed so far in the next one (atomic)
+//   ctl[2] plies expanded                   ctl[3] overflow flag (next frontier > capacity)     ctl[4] total (atomic)
+// Frontiers ping-pong between buf[0] and buf[1] (SoA with stride `cap`); the current one is buf[ctl[2] & 1].
+// does the next ply still expand breadth-first?  Yes while the frontier is small, or while the remaining depth is
+// more than one lane's stack can walk; never beyond depth-1 plies (the last ply is always counted by the walk).
+__device__ __forceinline__ bool bfs_active(const unsigned long long* ctl, long long min_frontier, int depth) {
+  const int plies = (int)ctl[2];
+  if (ctl[3] || plies >= depth - 1) return false;
+  return (long long)ctl[0] < min_frontier || depth - plies > PERFT_MAX_DEPTH;
+}
+
+__global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
+                                                         unsigned long long* __restrict__ ctl, long long min_frontier,
+                                                         int depth) {
+  if (!bfs_active(ctl, min_frontier, depth)) return;                  // uniform for the whole grid
+  const long long n = (long long)ctl[0];
+  const int plies = (int)ctl[2];
+  const u64* in = (plies & 1) ? buf1 : buf0;
+  u64* out = (plies & 1) ? buf0 : buf1;
+  const int lane = threadIdx.x & 31;
+  const long long n_pad = (n + 31) & ~31LL;                            // whole warps stay together for the shuffles
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x) {
+    u16 local[MAX_MOVES];
+    StoreSink s{local, 0};
+    Board b;
+    if (i < n) {
+      b = load_soa(in, cap, i);
+      generate_legal(b, s);
+    }
+    int pre = s.n;                                                     // inclusive prefix sum over the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, off);
+      if (lane >= off) pre += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+    unsigned long long base = 0;
+    if (lane == 0 && warp_total) base = atomicAdd(&ctl[1], (unsigned long long)warp_total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base + warp_total > (unsigned long long)cap) {
+      if (lane == 0) ctl[3] = 1;
+      continue;
+    }
+    const long long o = (long long)base + pre - s.n;
+    for (int k = 0; k < s.n; ++k) {
+      Board c = b;
+      make_move(c, local[k]);
+      store_soa(out, cap, o + k, c);
+    }
+  }
+}
+__global__ void k_bfs_commit(unsigned long long* __restrict__ ctl, long long min_frontier, int depth) {
+  if (!bfs_active(ctl, min_frontier, depth)) return;
+  ctl[0] = ctl[1];
+  ctl[1] = 0;
+  ctl[2] += 1;
+}
+__global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
+                                                            long long cap, unsigned long long* __restrict__ ctl, int depth,
+                                                            int bulk) {
+  if (ctl[3]) return;
+  const long long n = (long long)ctl[0];
+  const int plies = (int)ctl[2];
+  const u64* in = (plies & 1) ? buf1 : buf0;
+  const int remaining = depth - plies;
+  unsigned long long mine = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    mine += remaining <= 0 ? 1ull : perft_lane(load_soa(in, cap, i), remaining, bulk);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&ctl[4], mine);
 }
 
 // ---- one breadth-first ply ----------------------------------------------------------------------------
@@ -192,6 +275,36 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
   }
   LaunchScope ls(e, KC_MOVEGEN);
   k_perft<<<div_up(n, RULES_BLOCK), RULES_BLOCK, 0, e->stream>>>(boards, n, depth, bulk, nodes);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+// enqueues the whole device-driven perft of the root record already stored at buf0[k*cap] (k = 0..8); ctl is zeroed here
+int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl, int depth, int bulk,
+                      long long min_frontier) {
+  if (depth < 0 || depth > 64) {
+    set_error("crl_perft_root_host: depth %d is not supported", depth);
+    return CRL_EINVAL;
+  }
+  CRL_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), e->stream));
+  const unsigned long long one = 1;
+  CRL_CUDA(cudaMemcpyAsync(ctl, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
+  const int max_plies = depth - 1 > 0 ? depth - 1 : 0;
+  const int max_grid = 148 * 12;
+  long long bound = 1;
+  for (int ply = 0; ply < max_plies; ++ply) {
+    // boards that can exist at this ply: <= 218^ply and, once the frontier is large enough, expansion stops
+    const int grid = (int)(div_up(bound, RULES_BLOCK) < max_grid ? div_up(bound, RULES_BLOCK) : max_grid);
+    {
+      LaunchScope ls(e, KC_MOVEGEN, 2);
+      k_bfs_ply<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth);
+      k_bfs_commit<<<1, 1, 0, e->stream>>>(ctl, min_frontier, depth);
+      CRL_CUDA(cudaGetLastError());
+    }
+    bound = bound * 218 < cap ? bound * 218 : cap;
+  }
+  LaunchScope ls(e, KC_MOVEGEN);
+  const int grid = (int)(div_up(bound, RULES_BLOCK) < max_grid * 4 ? div_up(bound, RULES_BLOCK) : max_grid * 4);
+  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

@@ -87,6 +87,17 @@ class Engine:
         check(self.lib.crl_perft(self.h, _ptr(boards_t), n, int(depth), int(bool(bulk)), _ptr(nodes)))
         return nodes
 
+    def perft_root(self, record, depth, bulk=True, min_frontier=1 << 20):
+        """perft(depth) of one position in ONE call: device-side breadth-first plies to >= min_frontier boards, then a
+        depth-first walk per lane.  Returns (total, lanes, bfs_plies)."""
+        rec = np.ascontiguousarray(np.asarray(record, dtype=np.uint64).reshape(9))
+        total = ctypes.c_uint64(0)
+        lanes = ctypes.c_int64(0)
+        plies = ctypes.c_int32(0)
+        check(self.lib.crl_perft_root_host(self.h, _np(rec, ctypes.c_uint64), int(depth), int(bool(bulk)), int(min_frontier),
+                                           ctypes.byref(total), ctypes.byref(lanes), ctypes.byref(plies)))
+        return int(total.value), int(lanes.value), int(plies.value)
+
     def expand_frontier(self, boards_t):
         """One breadth-first ply: returns the SoA tensor of all children (python-chess move order per parent)."""
         n = boards_t.shape[1]

@@ -81,6 +81,13 @@ int crl_movegen(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* move
 int crl_make_moves(crl_engine* e, uint64_t* boards_dev, int n, const uint16_t* moves_dev);
 /* perft: each lane walks its own subtree depth-first; bulk != 0 counts the last ply without making moves */
 int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int bulk, uint64_t* nodes_dev);
+/* perft of ONE position in one call, no host round trip between plies: breadth-first plies on the device (children
+ * placed with warp-aggregated atomics, arbitrary order) until the frontier holds >= min_frontier boards, then one
+ * depth-first walk per lane (bulk as in crl_perft).  root_host [9] (AoS record).  Outputs: *total_host = perft(depth);
+ * optional *lanes_host = boards in the final frontier, *bfs_plies_host = plies expanded breadth-first.
+ * The frontier buffers are owned by the engine and grow on demand (CRL_ENOMEM if they cannot). */
+int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier,
+                        uint64_t* total_host, int64_t* lanes_host, int32_t* bfs_plies_host);
 /* one breadth-first ply: children of board i are written at offsets_dev[i] (exclusive scan of counts).
  * Call with out_dev == NULL to get counts only. */
 int crl_expand_frontier(crl_engine* e, const uint64_t* boards_dev, int n, const int64_t* offsets_dev,

@@ -183,3 +183,21 @@ def test_game_results_along_golden_games(engine1, golden_dir):
         assert r["accepted"].all() and r["result"] == c["final_result"], c["name"]
         last = c["trace"][-1]
         assert [B.move_to_uci(m) for m in r["legal"]] == last["legal"]
+
+
+@pytest.mark.parametrize("fen,expected", list(PERFT5.items()) + list(EXTRA.items()))
+def test_perft_root_device_driven(engine1, fen, expected):
+    """crl_perft_root_host: breadth-first plies on the device (atomic placement, no host round trip) + per-lane walk
+    give the published totals for every split between breadth-first plies and walk depth, bulk or not, including the
+    capacity-overflow retry (Kiwipete: 2,039 boards < 4,096 -> 97,862 > the initial 65,536-board buffers)."""
+    rec = B.record_from_fen(fen)
+    for depth, want in enumerate(expected[:5], start=1):
+        for min_frontier, bulk in ((1, True), (300, False), (4096, True), (1 << 20, True)):
+            if (not bulk and want > 5_000_000) or (min_frontier == 1 and want > 200_000):
+                continue                      # a single lane walking millions of nodes only tests patience
+            total, lanes, plies = engine1.perft_root(rec, depth, bulk=bulk, min_frontier=min_frontier)
+            assert total == want, (fen, depth, min_frontier, bulk, total, want)
+            assert 0 <= plies <= depth - 1 and lanes >= 1
+            if min_frontier == 1:
+                assert plies == 0 and lanes == 1
+    assert engine1.perft_root(rec, 0)[0] == 1
