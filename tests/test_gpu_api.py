@@ -211,6 +211,25 @@ def test_c_abi_argument_errors():
     assert (e.root_stats(want=("visits",))["root_visits"] == 9).all()
     with pytest.raises(_lib.CrlError):
         e.games_set(np.tile(B.record_from_fen(), (3, 1)))                            # more games than lanes
+    with pytest.raises(_lib.CrlError):
+        e.games_set_active([1, 1, 1])                                               # more lanes than the engine has
+    with pytest.raises(_lib.CrlError):
+        e.perft_root(B.record_from_fen(), -1)                                       # negative depth
+    with pytest.raises(_lib.CrlError):
+        e.perft_root(B.record_from_fen(), 3, min_frontier=0)                        # empty frontier target
+    assert lib.crl_game_replay_records_host(e.h, None, None, 0, None, None, None, None, None, None) == -1
+    # parking a lane: no search, no move, record still readable; resuming brings it back
+    e.games_set(np.tile(B.record_from_fen(), (2, 1)))
+    e.games_set_active([0], first=1)
+    e.mcts_begin_move()
+    e.mcts_simulate(6)
+    st = e.root_stats(want=("visits",))
+    assert st["root_visits"][0] == 7 and st["n_children"][1] == 0 and st["root_visits"][1] == 0
+    assert (e.games_get()[0][1] == B.record_from_fen()).all()
+    e.games_set_active([1], first=1)
+    e.mcts_begin_move()
+    e.mcts_simulate(6)
+    assert (e.root_stats(want=("visits",))["root_visits"] == 7).all()
     e.close()
 
 
