@@ -98,7 +98,9 @@ def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device
     lane_game = list(range(lanes))                               # which game runs in which lane
     next_game = lanes
     records = [None] * n_games
-    cap = None if max_moves is None else 2 * max_moves
+    # the engine's move lists hold 2,048 plies per game: a game that gets there is stored unfinished instead of
+    # failing the whole run (the fifty-move claim ends games long before that in practice)
+    cap = 2040 if max_moves is None else min(2040, 2 * max_moves)
     steps = 0
     while True:
         again, parked = [], []
