@@ -1002,19 +1002,21 @@ k_trunk(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __res
 // the epilogue un-permutes when it computes its global row.  Per (tile, layer) a CTA now reads 4 x 25.6 KB of
 // activations instead of 36 x 16 KB; the weight stream (36 x 16 KB) is unchanged and gets its own, deeper ring.
 // ======================================================================================================
-static constexpr int T4_NA = 3;                           // padded-image slots
-static constexpr int T4_NB = 7;                           // weight stages
+// ring sizes are template parameters: T4_NA padded-image slots, T4_NB weight stages (default 3 / 7)
 static constexpr int T4_IMG_ROWS = 200;                   // 10 x 2 x 10
 static constexpr int T4_IMG_BYTES = T4_IMG_ROWS * 128;    // 25,600
 static constexpr int T4_A_SLOT = 26 * 1024;               // slot pitch (1,024-byte aligned)
 static constexpr int T4_B_BYTES = 128 * BLOCK_K * 2;      // 16 KB: this CTA's half of the 256 filters
-static constexpr int T4_SMEM_BYTES = 1024 + T4_NA * T4_A_SLOT + T4_NB * T4_B_BYTES + 2 * TILE_N * 4 + 3 * 256 * 4 + 64 + 512;
+constexpr int t4_smem_bytes(int na, int nb) {
+  return 1024 + na * T4_A_SLOT + nb * T4_B_BYTES + 2 * TILE_N * 4 + 3 * 256 * 4 + 64 + 512;
+}
 
 // K-major SWIZZLE_128B descriptor with an explicit stride between 8-row groups
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+template <int T4_NA, int T4_NB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __restrict__ maps,
          const LayerDesc* __restrict__ layers, TrunkParams p) {
@@ -1370,6 +1372,7 @@ struct NetWeights {
   CUtensorMap map_pf, map_wp;
   // v4 (tower kernel with the padded-image A operand reused across the nine taps)
   bool use_trunk4 = true;
+  int t4_ring = 0;                          // index into the instantiated (image slots, weight stages) pairs
   CUtensorMap map_act4[2];
   CUtensorMap map_planes4;
   CUtensorMap* d_maps4 = nullptr;
@@ -1493,7 +1496,15 @@ int net_create(crl_engine_impl* e) {
   CRL_CUDA(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_conv_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
-  CRL_CUDA(cudaFuncSetAttribute(k_trunk4, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(3, 7)));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(3, 8)));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4<2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(2, 9)));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(2, 10)));
+  {
+    const char* r = getenv("CRL_T4_RING");   // tuning knob: 0 = 3/7 (default), 1 = 3/8, 2 = 2/9, 3 = 2/10
+    nw->t4_ring = r ? atoi(r) : 0;
+    if (nw->t4_ring < 0 || nw->t4_ring > 3) nw->t4_ring = 0;
+  }
   {
     // tensor-map table + layer table for the whole-tower kernel
     const char* nt = getenv("CRL_NO_TRUNK");
@@ -1793,9 +1804,15 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     if (pairs < 1) pairs = 1;
     {
       LaunchScope ls(e, KC_CONV);
-      if (nw->use_trunk4)
-        k_trunk4<<<2 * pairs, CONV_THREADS, T4_SMEM_BYTES, e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp);
-      else
+      if (nw->use_trunk4) {
+        const dim3 grid(2 * pairs), block(CONV_THREADS);
+        switch (nw->t4_ring) {
+          case 1: k_trunk4<3, 8><<<grid, block, t4_smem_bytes(3, 8), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
+          case 2: k_trunk4<2, 9><<<grid, block, t4_smem_bytes(2, 9), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
+          case 3: k_trunk4<2, 10><<<grid, block, t4_smem_bytes(2, 10), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
+          default: k_trunk4<3, 7><<<grid, block, t4_smem_bytes(3, 7), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
+        }
+      } else
         k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
       CRL_CUDA(cudaGetLastError());
     }
