@@ -150,8 +150,8 @@ def perft_metric(engine):
 
     total_nodes, total_ms = 0, 0.0
     for name, fen, want in (("start", B.STARTING_FEN, 4865609), ("kiwipete", KIWI, 193690690)):
-        ms, (lanes, plies) = timed_root(fen, 5, want, True, 65536)
-        ms_nb, _ = timed_root(fen, 5, want, False, 65536)
+        ms, (lanes, plies) = timed_root(fen, 5, want, True, 1 << 20)       # >= 65,536 boards: 197,281 / 4,085,603 lanes
+        ms_nb, _ = timed_root(fen, 5, want, False, 1 << 20)
         out[name] = {"nodes": want, "depth": 5, "ms": round(ms, 4), "nodes_per_s": want / ms * 1e3, "lanes": lanes,
                      "breadth_first_plies": plies, "leaf_bulk_counting": True,
                      "headline": "one crl_perft_root_host call: device-side frontier expansion + per-lane walk, leaf bulk counting",
@@ -174,13 +174,14 @@ def perft_metric(engine):
         total_ms += ms
     out["nodes_per_s"] = total_nodes / total_ms * 1e3
     # sustained throughput: two plies deeper (depth 5 is over in a fraction of a millisecond).  The breadth-first
-    # frontier is grown to >= 1 Mi boards (start: 4,865,609 at depth 5, Kiwipete: 4,085,603 at depth 4) so that every lane
-    # walks only two plies: sibling lanes then do nearly the same amount of work and warps stay converged -- 2.2-2.5x the
-    # throughput of 65,536-board frontiers with three plies per lane (scripts/perft_frontier_probe.py).
+    # frontier is grown all the way to the last-but-one ply (start: 119,060,324 boards, Kiwipete: 193,690,690 -- 8.6 / 13.9
+    # GB of HBM) so that the walk is one count-only move generation per lane: every lane does the same amount of work and
+    # warps stay converged -- about 3x the throughput of 65,536-board frontiers with three plies per lane
+    # (scripts/perft_root_probe.py --deep).
     deep_nodes, deep_ms = 0, 0.0
     for name, fen, depth, want in (("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
-        ms, (lanes, plies) = timed_root(fen, depth, want, True, 1 << 20, reps=2)
-        ms_nb, _ = timed_root(fen, depth, want, False, 1 << 20, reps=1)
+        ms, (lanes, plies) = timed_root(fen, depth, want, True, 1 << 26, reps=2)
+        ms_nb, _ = timed_root(fen, depth, want, False, 1 << 26, reps=1)
         out[name] = {"nodes": want, "depth": depth, "lanes": lanes, "breadth_first_plies": plies, "plies_per_lane": depth - plies,
                      "ms_bulk": round(ms, 3), "nodes_per_s_bulk": want / ms * 1e3,
                      "ms_no_bulk": round(ms_nb, 3), "nodes_per_s_no_bulk": want / ms_nb * 1e3}

@@ -373,6 +373,8 @@ int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int
   // quiet position; a bushier frontier overflows, which is detected on the device and retried with four times the room
   long long cap = min_frontier * 16;
   if (cap < (1 << 16)) cap = 1 << 16;
+  const long long cap_max = 320LL << 20;       // 320 Mi boards = 23 GB per buffer: holds Kiwipete's depth-5 frontier
+  if (cap > cap_max) cap = min_frontier * 2 > cap_max ? min_frontier * 2 : cap_max;
   for (int attempt = 0; attempt < 4; ++attempt, cap *= 4) {
     if (cap > e->perft_cap) {
       for (int i = 0; i < 2; ++i) {

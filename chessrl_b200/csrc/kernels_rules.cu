@@ -164,44 +164,104 @@ __device__ __forceinline__ bool bfs_active(const unsigned long long* ctl, long l
   return (long long)ctl[0] < min_frontier || depth - plies > PERFT_MAX_DEPTH;
 }
 
+// Each warp takes 32 parent boards per round.  Phase 1: one lane per parent generates its legal moves into a shared-
+// memory row (and parks the parent record there).  Phase 2: the warp's children are dealt round-robin to the lanes --
+// child j of the warp -> lane j % 32, its parent found by a 5-step binary search over the warp's prefix sums -- so every
+// lane makes one move per step and the 72-byte records of 32 consecutive children are stored with nine fully coalesced
+// 256-byte writes (one lane writing all children of its own parent scatters 8-byte stores over 32 different rows).
+static constexpr int BFS_CAP = 96;          // moves per parent staged in shared memory; the (rare) rest stays with its lane
+
+struct BfsSink {
+  static constexpr bool kCounting = false;
+  u16* row;        // shared-memory row of this parent
+  u16* spill;      // this lane's local overflow list (moves BFS_CAP ..)
+  int n;
+  __device__ __forceinline__ void add(int) {}
+  __device__ __forceinline__ void put(u16 m) {
+    if (n < BFS_CAP) row[n] = m;
+    else spill[n - BFS_CAP] = m;
+    ++n;
+  }
+  __device__ __forceinline__ void put_set(int from, u64 targets) {   // MSB -> LSB
+    while (targets) {
+      int t = msb64(targets);
+      targets ^= bit(t);
+      put(mk_move(from, t, 0));
+    }
+  }
+};
+
 __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
                                                          unsigned long long* __restrict__ ctl, long long min_frontier,
                                                          int depth) {
+  __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
+  __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
+  __shared__ int s_pre[RULES_BLOCK / 32][33];
   if (!bfs_active(ctl, min_frontier, depth)) return;                  // uniform for the whole grid
   const long long n = (long long)ctl[0];
   const int plies = (int)ctl[2];
   const u64* in = (plies & 1) ? buf1 : buf0;
   u64* out = (plies & 1) ? buf0 : buf1;
-  const int lane = threadIdx.x & 31;
-  const long long n_pad = (n + 31) & ~31LL;                            // whole warps stay together for the shuffles
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_pad = (n + 31) & ~31LL;                            // whole warps stay together
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x) {
-    u16 local[MAX_MOVES];
-    StoreSink s{local, 0};
+    // ---- phase 1: one parent per lane ----
+    u16 spill[MAX_MOVES - BFS_CAP];
+    BfsSink sink{s_moves[warp][lane], spill, 0};
     Board b;
     if (i < n) {
       b = load_soa(in, cap, i);
-      generate_legal(b, s);
+      generate_legal(b, sink);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_board[warp][k][lane] = b.bb[k];
+      s_board[warp][8][lane] = b.meta;
     }
-    int pre = s.n;                                                     // inclusive prefix sum over the warp
+    int pre = sink.n;                                                  // inclusive prefix sum over the warp
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, pre, off);
       if (lane >= off) pre += v;
     }
     const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+    s_pre[warp][lane] = pre - sink.n;
+    if (lane == 31) s_pre[warp][32] = warp_total;
     unsigned long long base = 0;
     if (lane == 0 && warp_total) base = atomicAdd(&ctl[1], (unsigned long long)warp_total);
     base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
     if (base + warp_total > (unsigned long long)cap) {
       if (lane == 0) ctl[3] = 1;
+      __syncwarp();
       continue;
     }
-    const long long o = (long long)base + pre - s.n;
-    for (int k = 0; k < s.n; ++k) {
-      Board c = b;
-      make_move(c, local[k]);
-      store_soa(out, cap, o + k, c);
+    // ---- phase 2: children dealt round-robin ----
+    for (int j = lane; j < warp_total; j += 32) {
+      int lo = 0, hi = 32;
+#pragma unroll
+      for (int step = 0; step < 5; ++step) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pre[warp][mid] <= j) lo = mid;
+        else hi = mid;
+      }
+      const int k = j - s_pre[warp][lo];
+      if (k >= BFS_CAP) continue;                                      // stays with its parent's lane (phase 3)
+      Board c;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) c.bb[w] = s_board[warp][w][lo];
+      c.meta = s_board[warp][8][lo];
+      make_move(c, s_moves[warp][lo][k]);
+      store_soa(out, cap, (long long)base + j, c);
     }
+    // ---- phase 3: parents with more than BFS_CAP moves finish their own list ----
+    if (sink.n > BFS_CAP) {
+      const long long o = (long long)base + pre - sink.n;
+      for (int k = BFS_CAP; k < sink.n; ++k) {
+        Board c = b;
+        make_move(c, spill[k - BFS_CAP]);
+        store_soa(out, cap, o + k, c);
+      }
+    }
+    __syncwarp();                                                      // the rows are reused by the next round
   }
 }
 __global__ void k_bfs_commit(unsigned long long* __restrict__ ctl, long long min_frontier, int depth) {
