@@ -256,3 +256,24 @@ def test_cli_selfplay_then_supervised(tmp_path):
     supervised.main([d, os.path.join(d, "gameplays.json"), "--epochs", "1", "--bs", "2"])
     w1 = Agent(True, weights=path).model.weights
     assert any(not np.array_equal(a, b) for a, b in zip(w0, w1))
+
+
+def test_whole_selfplay_games_replay_under_the_oracle():
+    """Complete lockstep games with the real network (slot refill, both colours): every stored move is legal in the
+    python-chess restatement, the stored result is Game.get_result of the final position, and unfinished positions
+    along the way are not terminal."""
+    from chessrl_b200 import selfplay
+    from chessrl_b200.agent import Agent
+    agent = Agent(True)
+    data = selfplay.play_games_lockstep(agent.model, 10, sims=6, lanes=4, noise=True, seed=11)
+    assert len(data) == 10
+    finished = 0
+    for g in data.games:
+        h = g.get_history()
+        og = O.OGame()
+        for i, m in enumerate(h["moves"]):
+            assert og.get_result() is None, (i, h["moves"][:i])
+            assert og.move(m), (i, m)
+        assert og.get_result() == h["result"]
+        finished += h["result"] is not None
+    assert finished >= 8          # only a 2,040-ply game would be stored unfinished
