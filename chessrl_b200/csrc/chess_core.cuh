@@ -95,6 +95,27 @@ CRL_HD u64 brev64(u64 x) {
 #endif
 }
 CRL_HD u64 bit(int sq) { return 1ULL << sq; }
+// 32-bit halves: a 64-bit count-leading-zeros / variable shift costs several 32-bit instructions on the GPU, so the
+// hot loops that walk a set from its most significant bit down do it one word at a time
+CRL_HD int msb32(u32 x) {
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)x);
+#else
+  return 31 - __builtin_clz(x);
+#endif
+}
+// removes and returns the most significant set bit (x != 0)
+CRL_HD int pop_msb(u64& x) {
+  const u32 hi = (u32)(x >> 32);
+  if (hi) {
+    const int t = msb32(hi);
+    x ^= (u64)(1u << t) << 32;
+    return t + 32;
+  }
+  const int t = msb32((u32)x);
+  x ^= (u64)(1u << t);
+  return t;
+}
 
 static const u64 FILE_A = 0x0101010101010101ULL;
 static const u64 FILE_B = FILE_A << 1;
@@ -187,17 +208,9 @@ CRL_HD u64 attack_map(const Board& b, u64 occ, int by_white) {
   u64 a = pawn_attacks_set(b.bb[PAWN] & side, by_white) | knight_attacks_set(b.bb[KNIGHT] & side) |
           king_attacks_set(b.bb[KING] & side);
   u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & side;
-  while (rq) {
-    int s = msb64(rq);
-    rq ^= bit(s);
-    a |= rook_attacks(s, occ);
-  }
+  while (rq) a |= rook_attacks(pop_msb(rq), occ);
   u64 bq = (b.bb[BISHOP] | b.bb[QUEEN]) & side;
-  while (bq) {
-    int s = msb64(bq);
-    bq ^= bit(s);
-    a |= bishop_attacks(s, occ);
-  }
+  while (bq) a |= bishop_attacks(pop_msb(bq), occ);
   return a;
 }
 
@@ -214,11 +227,17 @@ struct StoreSink {
   int n;
   CRL_HD void add(int) {}
   CRL_HD void put(u16 m) { out[n++] = m; }
-  CRL_HD void put_set(int from, u64 targets) {   // MSB -> LSB
-    while (targets) {
-      int t = msb64(targets);
-      targets ^= bit(t);
-      out[n++] = mk_move(from, t, 0);
+  CRL_HD void put_set(int from, u64 targets) {   // MSB -> LSB, one 32-bit word at a time
+    u32 hi = (u32)(targets >> 32), lo = (u32)targets;
+    while (hi) {
+      const int t = msb32(hi);
+      hi ^= 1u << t;
+      out[n++] = (u16)(from | ((t + 32) << 6));
+    }
+    while (lo) {
+      const int t = msb32(lo);
+      lo ^= 1u << t;
+      out[n++] = (u16)(from | (t << 6));
     }
   }
 };
@@ -282,8 +301,7 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
     u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & them, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & them;
     u64 snipers = ((rank_mask(ksq) | file_mask(ksq)) & rq) | ((diag_mask(ksq) | anti_mask(ksq)) & bq);
     while (snipers) {
-      int s = msb64(snipers);
-      snipers ^= bit(s);
+      const int s = pop_msb(snipers);
       u64 mid = between(ksq, s) & occ;
       if (mid && !(mid & (mid - 1))) pinned |= mid;
     }
@@ -311,9 +329,8 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   u64 officers = us & ~b.bb[PAWN];
   if (checkers) officers &= ~kbit;
   while (officers) {
-    int from = msb64(officers);
-    u64 fb = bit(from);
-    officers ^= fb;
+    const int from = pop_msb(officers);
+    const u64 fb = bit(from);
     u64 t;
     if (fb & b.bb[KNIGHT]) t = knight_attacks_set(fb);
     else if (fb & b.bb[KING]) t = king_targets & ~danger;
@@ -348,24 +365,21 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
     sink.add(popc64(tl) + popc64(tr) + 3 * (popc64(tl & promo_rank) + popc64(tr & promo_rank)));
     u64 src = pawns & pinned;
     while (src) {
-      int from = msb64(src);
-      u64 fb = bit(from);
-      src ^= fb;
+      const int from = pop_msb(src);
+      const u64 fb = bit(from);
       u64 t = pawn_attacks_set(fb, white) & them & target & line_through(ksq, from);
       sink.add(popc64(t) + 3 * popc64(t & promo_rank));
     }
   } else {
     u64 src = pawns;
     while (src) {
-      int from = msb64(src);
-      u64 fb = bit(from);
-      src ^= fb;
+      const int from = pop_msb(src);
+      const u64 fb = bit(from);
       u64 t = pawn_attacks_set(fb, white) & them & target;
       if (fb & pinned) t &= line_through(ksq, from);
       if (t & promo_rank) {
         while (t) {
-          int to = msb64(t);
-          t ^= bit(to);
+          const int to = pop_msb(t);
           sink.put(mk_move(from, to, QUEEN));
           sink.put(mk_move(from, to, ROOK));
           sink.put(mk_move(from, to, BISHOP));
@@ -401,10 +415,8 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
       sink.add(popc64(single) + 3 * popc64(single & promo_rank) + popc64(dbl));
     } else {
       while (single) {
-        int to = msb64(single);
-        u64 tb = bit(to);
-        single ^= tb;
-        if (tb & promo_rank) {
+        const int to = pop_msb(single);
+        if ((white ? to >= 56 : to < 8)) {
           sink.put(mk_move(to + back, to, QUEEN));
           sink.put(mk_move(to + back, to, ROOK));
           sink.put(mk_move(to + back, to, BISHOP));
@@ -414,8 +426,7 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
         }
       }
       while (dbl) {
-        int to = msb64(dbl);
-        dbl ^= bit(to);
+        const int to = pop_msb(dbl);
         sink.put(mk_move(to + 2 * back, to, 0));
       }
     }
@@ -429,8 +440,7 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
     if (allowed) {
       u64 cap = pawns & pawn_attacks_set(bit(ep), !white) & (white ? (0xFFULL << 32) : (0xFFULL << 24));
       while (cap) {
-        int from = msb64(cap);
-        cap ^= bit(from);
+        const int from = pop_msb(cap);
         if (ep_capture_safe(b, from, ep, white, ksq)) {
           sink.put(mk_move(from, ep, 0));
           info.ep_legal = 1;

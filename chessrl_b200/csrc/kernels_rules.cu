@@ -28,11 +28,17 @@ struct StageSink {
     else grow[n] = m;
     ++n;
   }
-  __device__ __forceinline__ void put_set(int from, u64 targets) {   // MSB -> LSB
-    while (targets) {
-      int t = msb64(targets);
-      targets ^= bit(t);
-      put(mk_move(from, t, 0));
+  __device__ __forceinline__ void put_set(int from, u64 targets) {   // MSB -> LSB, one 32-bit word at a time
+    u32 hi = (u32)(targets >> 32), lo = (u32)targets;
+    while (hi) {
+      const int t = msb32(hi);
+      hi ^= 1u << t;
+      put((u16)(from | ((t + 32) << 6)));
+    }
+    while (lo) {
+      const int t = msb32(lo);
+      lo ^= 1u << t;
+      put((u16)(from | (t << 6)));
     }
   }
 };
@@ -51,6 +57,9 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_movegen(const u64* __restrict__
     cnt = sink.n;
     counts[i] = cnt;
     if (flags) flags[i] = (u8)((gi.in_check ? 1 : 0) | (gi.ep_legal ? 2 : 0));
+    // pad the staged row to a whole quad so the copy-out below moves only full 8-byte groups (the up to three
+    // entries past the count are CRL_MOVE_NONE)
+    for (int k = cnt; (k & 3) && k < MG_CAP; ++k) s_moves[warp][lane][k] = MOVE_NONE;
   }
   __syncwarp();
   const int base = blockIdx.x * blockDim.x + warp * 32;
@@ -64,12 +73,8 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_movegen(const u64* __restrict__
     const u16* src = s_moves[warp][l];
     u16* dst = moves + (long long)(base + l) * MAX_MOVES;
     for (int k = sub * 4; k < c; k += 16) {
-      if (k + 4 <= c) {
-        const u32 a = *reinterpret_cast<const u32*>(src + k), b2 = *reinterpret_cast<const u32*>(src + k + 2);
-        *reinterpret_cast<uint2*>(dst + k) = make_uint2(a, b2);
-      } else {
-        for (int j = k; j < c; ++j) dst[j] = src[j];
-      }
+      const u32 a = *reinterpret_cast<const u32*>(src + k), b2 = *reinterpret_cast<const u32*>(src + k + 2);
+      *reinterpret_cast<uint2*>(dst + k) = make_uint2(a, b2);
     }
   }
 }
@@ -182,11 +187,17 @@ struct BfsSink {
     else spill[n - BFS_CAP] = m;
     ++n;
   }
-  __device__ __forceinline__ void put_set(int from, u64 targets) {   // MSB -> LSB
-    while (targets) {
-      int t = msb64(targets);
-      targets ^= bit(t);
-      put(mk_move(from, t, 0));
+  __device__ __forceinline__ void put_set(int from, u64 targets) {   // MSB -> LSB, one 32-bit word at a time
+    u32 hi = (u32)(targets >> 32), lo = (u32)targets;
+    while (hi) {
+      const int t = msb32(hi);
+      hi ^= 1u << t;
+      put((u16)(from | ((t + 32) << 6)));
+    }
+    while (lo) {
+      const int t = msb32(lo);
+      lo ^= 1u << t;
+      put((u16)(from | (t << 6)));
     }
   }
 };
