@@ -9,6 +9,8 @@ import pytest
 import torch
 
 import chessrl_oracle as O
+import perft_kats
+import position_fuzz
 from chessrl_b200 import boards as B
 
 pytestmark = pytest.mark.gpu
@@ -201,3 +203,65 @@ def test_perft_root_device_driven(engine1, fen, expected):
             if min_frontier == 1:
                 assert plies == 0 and lanes == 1
     assert engine1.perft_root(rec, 0)[0] == 1
+
+
+def test_perft_rule_corner_positions(engine1):
+    """perft_kats.EDGE (ep pins, castling into / through check, promotions in and out of check, stalemate traps):
+    shallow depths with one lane per root, every depth through the device-driven breadth-first + walk path."""
+    recs = np.stack([B.record_from_fen(fen) for fen, _ in perft_kats.EDGE])
+    t = engine1.boards_to_device(recs)
+    for d in range(1, 5):
+        got = engine1.perft(t, d, bulk=bool(d & 1)).cpu().numpy()
+        for (fen, exp), g in zip(perft_kats.EDGE, got):
+            assert int(g) == exp[d - 1], (fen, d)
+    for fen, exp in perft_kats.EDGE:
+        rec = B.record_from_fen(fen)
+        for depth, want in enumerate(exp, start=1):
+            total, lanes, plies = engine1.perft_root(rec, depth, bulk=True, min_frontier=4096)
+            assert total == want, (fen, depth, total, want)
+        total, _, _ = engine1.perft_root(rec, len(exp) - 1, bulk=False, min_frontier=256)
+        assert total == exp[-2], fen
+
+
+def test_movegen_most_legal_moves(engine1):
+    """The two 218-move positions: list and python-chess ORDER, policy indices, one breadth-first ply."""
+    recs = np.stack([B.record_from_fen(f) for f in perft_kats.MAX_MOVES])
+    t = engine1.boards_to_device(recs)
+    mv, cn, fl = engine1.movegen(t)
+    got = _moves_host(mv, cn)
+    idx = engine1.policy_index(mv, cn).cpu().numpy()
+    lab = O.label_index()
+    for fen, g, row in zip(perft_kats.MAX_MOVES, got, idx):
+        want = [m.uci() for m in chess.Board(fen).generate_legal_moves()]
+        assert len(g) == 218 and g == want
+        assert [int(x) for x in row[:218]] == [lab[m] for m in want]
+    kids, counts = engine1.expand_frontier(t)
+    assert counts.cpu().tolist() == [218, 218] and kids.shape[1] == 436
+    assert engine1.perft(t, 1).cpu().tolist() == [218, 218]
+
+
+def test_rules_on_unreachable_random_positions(engine1):
+    """800 seeded positions no game from the start reaches (position_fuzz: promoted material, castling rights, raw ep
+    squares): k_movegen lists in python-chess ORDER + flags, and every child of one breadth-first ply (k_bfs / make-move)
+    against the restatement."""
+    rng = random.Random(12)
+    cases = [position_fuzz.random_fen(rng) for _ in range(800)]
+    t = engine1.boards_to_device(np.stack([B.record_from_fen(fen) for fen, _ in cases]))
+    mv, cn, fl = engine1.movegen(t)
+    got, flags = _moves_host(mv, cn), fl.cpu().numpy()
+    for (fen, b), g, f in zip(cases, got, flags):
+        assert g == [m.uci() for m in b.generate_legal_moves()], fen
+        assert bool(f & 1) == b.is_check() and bool(f & 2) == b.has_legal_en_passant(), fen
+    kids, counts = engine1.expand_frontier(t)
+    assert counts.cpu().tolist() == [len(g) for g in got]
+    kid_recs = engine1.boards_to_host(kids)
+    _, _, kfl = engine1.movegen(kids)
+    kflags = kfl.cpu().numpy()
+    k = 0
+    for (fen, b), g in zip(cases, got):
+        for m in g:
+            b.push(chess.Move.from_uci(m))
+            assert B.fen_from_record(kid_recs[k], bool(kflags[k] & 2)) == b.fen(), (fen, m)
+            b.pop()
+            k += 1
+    assert k == kids.shape[1]

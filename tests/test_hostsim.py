@@ -11,6 +11,8 @@ import pytest
 
 import chessrl_oracle as O
 import hostsim
+import perft_kats
+import position_fuzz
 from chessrl_b200 import boards as B
 
 chess = O.chess
@@ -62,6 +64,57 @@ def test_device_core_perft(lib, fen, expected):
         if d <= 4:
             assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 0) == e       # every leaf generated / made (StoreSink)
     assert lib.hs_perft(rec.ctypes.data_as(u64p), 3, 0) == expected[2]      # without leaf bulk counting
+
+
+@pytest.mark.parametrize("fen,expected", perft_kats.EDGE)
+def test_device_core_perft_rule_corners(lib, fen, expected):
+    """Full published depth (the host build runs ~50 M nodes/s), with and without leaf bulk counting."""
+    rec = B.record_from_fen(fen)
+    for d, e in enumerate(expected, 1):
+        assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 1) == e, (fen, d)
+        if e <= 300_000:
+            assert lib.hs_perft(rec.ctypes.data_as(u64p), d, 0) == e, (fen, d)
+
+
+@pytest.mark.parametrize("fen", perft_kats.MAX_MOVES)
+def test_device_core_most_legal_moves(lib, fen):
+    """218 legal moves: same list, same ORDER as the python-chess restatement; children are all distinct."""
+    rec = B.record_from_fen(fen)
+    ml, chk, epl = movegen(lib, rec)
+    assert len(ml) == 218 and not chk and not epl
+    assert ml == [m.uci() for m in chess.Board(fen).generate_legal_moves()]
+    assert lib.hs_perft(rec.ctypes.data_as(u64p), 1, 1) == 218 and lib.hs_perft(rec.ctypes.data_as(u64p), 1, 0) == 218
+
+
+def test_device_core_on_unreachable_random_positions(lib):
+    """1,000 seeded positions that no game from the start reaches (position_fuzz): move list in python-chess ORDER,
+    check / legal-ep flags, FEN, and every child position (make-move) against the restatement."""
+    import random
+    rng = random.Random(11)
+    seen = {"ep": 0, "check": 0, "castle": 0, "promo": 0, "moves": 0}
+    for _ in range(1000):
+        fen, b = position_fuzz.random_fen(rng)
+        rec = B.record_from_fen(fen)
+        want = [m.uci() for m in b.generate_legal_moves()]
+        got, chk, epl = movegen(lib, rec)
+        assert got == want, fen
+        assert bool(chk) == b.is_check() and bool(epl) == b.has_legal_en_passant(), fen
+        assert B.fen_from_record(rec, epl) == b.fen(), fen
+        seen["ep"] += bool(epl)
+        seen["check"] += bool(chk)
+        for m in want:
+            child = rec.copy()
+            lib.hs_make(child.ctypes.data_as(u64p), B.uci_to_move(m))
+            mv = chess.Move.from_uci(m)
+            seen["castle"] += b.is_castling(mv)
+            seen["promo"] += len(m) == 5
+            b.push(mv)
+            ml2, _, epl2 = movegen(lib, child)
+            assert B.fen_from_record(child, epl2) == b.fen(), (fen, m)
+            assert len(ml2) == sum(1 for _ in b.generate_legal_moves()), (fen, m)
+            b.pop()
+        seen["moves"] += len(want)
+    assert seen["ep"] > 50 and seen["check"] > 200 and seen["castle"] > 50 and seen["promo"] > 200, seen
 
 
 def test_device_core_follows_oracle_along_games(lib, golden_dir):

@@ -7,6 +7,7 @@ import os
 import pytest
 
 import chessrl_oracle as O
+import perft_kats
 
 chess = O.chess
 
@@ -37,6 +38,24 @@ def test_perft_table(fen, expected):
     b = chess.Board(fen)
     for d, e in enumerate(expected, 1):
         assert perft(b, d) == e
+
+
+@pytest.mark.parametrize("fen,expected", perft_kats.EDGE)
+def test_perft_rule_corner_positions(fen, expected):
+    """En passant pins, castling through / into check, promotions in and out of check, stalemate traps."""
+    b = chess.Board(fen)
+    for d, e in enumerate(expected, 1):
+        if e > perft_kats.ORACLE_NODE_CAP:
+            break
+        assert perft(b, d) == e, (fen, d)
+
+
+@pytest.mark.parametrize("fen", perft_kats.MAX_MOVES)
+def test_most_legal_moves_of_any_position(fen):
+    ms = [m.uci() for m in chess.Board(fen).legal_moves]
+    assert len(ms) == 218 and len(set(ms)) == 218
+    idx = O.label_index()
+    assert all(m in idx for m in ms)                       # every one has a policy label
 
 
 def test_start_move_order_kat1():
