@@ -212,3 +212,40 @@ def test_lockstep_lanes_are_independent():
     for g in range(2, 64):
         assert (st["visits"][g] == st["visits"][g % 2]).all() and (st["values"][g] == st["values"][g % 2]).all()
     e.close()
+
+
+def test_search_from_unreachable_roots_matches_oracle():
+    """Lockstep search rooted at position_fuzz positions (terminal children, promotions, ep and castling inside the
+    tree, roots with up to ~90 legal moves), one position per lane: visit counts, value sums, results and
+    (move, reply) lines against the restated SelfPlayTree with the shared evaluator."""
+    import random
+    import position_fuzz
+    from chessrl_b200.engine import Engine
+    rng = random.Random(22)
+    for sims, seed, bits in ((33, 7, 24), (90, 401, 3), (150, 12, 11)):
+        fens = []
+        while len(fens) < 24:
+            fen, _ = position_fuzz.random_fen(rng)
+            if O.OGame(board=chess.Board(fen)).get_result() is None:
+                fens.append(fen)
+        e = Engine(max_games=len(fens), max_nodes=sims + 1, avg_moves=218)
+        e.set_evaluator(EVAL_HASH, seed, bits)
+        e.games_set(np.stack([B.record_from_fen(f) for f in fens]))
+        e.mcts_begin_move()
+        e.mcts_simulate(sims)
+        st = e.root_stats()
+        for g, fen in enumerate(fens):
+            ot = O.OSelfPlayTree(O.OGame(board=chess.Board(fen)))
+            ot.search_move(O.OAgent(O.hash_evaluator(seed, bits)), max_iters=sims, noise=False)
+            kids = ot.root.children
+            assert int(st["n_children"][g]) == len(kids) and int(st["root_visits"][g]) == ot.root.visits, fen
+            assert float(st["root_values"][g]) == float(ot.root.value), fen
+            for k, c in enumerate(kids):
+                assert int(st["visits"][g, k]) == c.visits and float(st["values"][g, k]) == float(c.value), (fen, k)
+                r = int(st["results"][g, k])
+                assert (None if r == B.RESULT_NONE else r) == c.state.get_result(), (fen, k)
+                line = [B.move_to_uci(st["moves"][g, k])]
+                if st["replies"][g, k] != B.MOVE_NONE:
+                    line.append(B.move_to_uci(st["replies"][g, k]))
+                assert line == [str(x) for x in c.state.board.move_stack], (fen, k)
+        e.close()

@@ -211,6 +211,44 @@ def test_device_tree_core_wave_mode_matches_reference(lib, golden_dir):
                 assert lib.hs_edge_score(V[k], W[k], Pr[k], Rs[k]) == float.fromhex(kid["score"])
 
 
+def test_device_tree_core_from_unreachable_roots(lib):
+    """Searches rooted at position_fuzz positions (terminal children, promotions, ep and castling inside the tree,
+    up to 90 legal moves at the root): visit counts, value sums, results and (move, reply) lines against the
+    restated SelfPlayTree with the shared evaluator."""
+    import random
+    tab = _label_table()
+    t = lib.hs_tree_new(1024, 1024 * 220, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    rng = random.Random(21)
+    searched = terminal_kids = 0
+    for _ in range(60):
+        fen, _b = position_fuzz.random_fen(rng)
+        sims, seed, bits = rng.choice([5, 33, 90]), rng.randrange(1, 1000), rng.choice([3, 11, 24])
+        g = O.OGame(board=chess.Board(fen))
+        if g.get_result() is not None:
+            continue
+        rec = B.record_from_fen(fen)
+        none = np.zeros(1, dtype=np.uint16)
+        assert lib.hs_game_set(t, rec.ctypes.data_as(u64p), none.ctypes.data_as(u16p), 0) == 0
+        assert lib.hs_search(t, sims, seed, bits) >> 24 == 0
+        ot = O.OSelfPlayTree(g)
+        ot.search_move(O.OAgent(O.hash_evaluator(seed, bits)), max_iters=sims, noise=False)
+        V, W, Pr = (ctypes.c_int * 256)(), (ctypes.c_double * 256)(), (ctypes.c_float * 256)()
+        M, R, Rs = (ctypes.c_uint16 * 256)(), (ctypes.c_uint16 * 256)(), (ctypes.c_int * 256)()
+        rv, rw = ctypes.c_int(), ctypes.c_double()
+        n = lib.hs_root_stats(t, V, W, Pr, M, R, Rs, ctypes.byref(rv), ctypes.byref(rw))
+        kids = ot.root.children
+        assert n == len(kids) and rv.value == ot.root.visits and rw.value == float(ot.root.value), fen
+        for k, c in enumerate(kids):
+            assert V[k] == c.visits and W[k] == float(c.value), (fen, k)
+            r = c.state.get_result()
+            terminal_kids += r is not None
+            assert (None if Rs[k] == 2 else Rs[k]) == r, (fen, k)
+            line = [B.move_to_uci(M[k])] + ([B.move_to_uci(R[k])] if R[k] != 0xFFFF else [])
+            assert line == [str(x) for x in c.state.board.move_stack], (fen, k)
+        searched += 1
+    assert searched >= 50 and terminal_kids >= 3
+
+
 def test_device_history_walk_matches_planes(lib):
     """The parent-chain walk used for history planes inside the tree reproduces the move-stack walk of
     netencoder._get_game_history for a node deep in a search."""
