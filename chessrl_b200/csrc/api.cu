@@ -201,8 +201,10 @@ int crl_create(crl_engine** out, int device, int max_games, int max_nodes, int a
 int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, int avg_moves, int max_inflight,
                   void* stream) {
   if (!out || max_games <= 0 || max_nodes <= 0 || max_inflight < 1 || max_inflight > CRL_MAX_INFLIGHT ||
-      (long long)max_games * max_inflight > (1ll << 24)) {
-    set_error("crl_create: bad arguments (max_games %d, max_nodes %d, max_inflight %d)", max_games, max_nodes, max_inflight);
+      (long long)max_games * max_inflight > (1ll << 24) || avg_moves > MAX_MOVES ||
+      ((long long)max_nodes + 1) * (avg_moves > 0 ? avg_moves : 64) > 0x7fffffffll) {   // per-game edge arena is int-indexed
+    set_error("crl_create: bad arguments (max_games %d, max_nodes %d, avg_moves %d, max_inflight %d)", max_games, max_nodes,
+              avg_moves, max_inflight);
     return CRL_EINVAL;
   }
   int n_dev = 0;

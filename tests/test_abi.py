@@ -55,3 +55,16 @@ def test_record_format_roundtrip():
     assert B.uci_to_move("00000") == B.MOVE_NONE and B.uci_to_move("e2e2") == B.MOVE_NONE
     # castling rights are cleaned like Board.clean_castling_rights()
     assert B.meta_fields(B.record_from_fen("4k3/8/8/8/8/8/8/4K2R w KQkq - 0 1")[8])["castle"] == 1
+
+
+def test_create_rejects_bad_arguments_before_touching_a_device():
+    """Argument validation of crl_create_ex comes first, so it is checkable without a GPU: negative status,
+    crl_last_error text, *out untouched."""
+    import ctypes
+    lib = _lib.load()
+    h = _lib.vp()
+    for games, nodes, avg, inflight in ((0, 16, 64, 1), (4, 0, 64, 1), (4, 16, 64, 0), (4, 16, 64, 10 ** 6),
+                                        (4, 16, 257, 1), (4, 1 << 24, 218, 1), (1 << 20, 16, 64, 32)):
+        assert lib.crl_create_ex(ctypes.byref(h), 0, games, nodes, avg, inflight, None) == -1, (games, nodes, avg, inflight)
+        assert b"bad arguments" in lib.crl_last_error() and not h.value
+    assert lib.crl_create_ex(None, 0, 4, 16, 64, 1, None) == -1

@@ -197,6 +197,8 @@ def test_c_abi_argument_errors():
     assert lib.crl_create_ex(ctypes.byref(h), 0, 4, 16, 64, 0, None) == -1          # max_inflight < 1
     assert lib.crl_create_ex(ctypes.byref(h), 0, 0, 16, 64, 1, None) == -1          # no lanes
     assert b"bad arguments" in lib.crl_last_error()
+    assert lib.crl_create_ex(ctypes.byref(h), 0, 4, 16, 257, 1, None) == -1         # more edge slots per node than moves exist
+    assert lib.crl_create_ex(ctypes.byref(h), 0, 4, 1 << 24, 218, 1, None) == -1    # per-game edge arena past int range
     e = Engine(max_games=2, max_nodes=8, max_inflight=2)
     e.set_evaluator(_lib.EVAL_HASH, 1, 24)
     with pytest.raises(_lib.CrlError):
