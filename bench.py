@@ -428,21 +428,21 @@ def run_reference(args, rank, world):
         return
     per_step = max(1.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
-        cpu_reference_sims(min(per_step, 2.0), 100)
+        cpu_reference_sims(min(per_step, 2.0), args.sims)
     # pick the arrangement once (short probe), then time the steps with it
-    best, one, par = cpu_baseline_best(min(per_step, 5.0))
+    best, one, par = cpu_baseline_best(min(per_step, 5.0), args.sims)
     parallel = best is par
     tot_s, tot_t, cores = 0, 0.0, 1
     for _ in range(args.steps):
         if parallel:
-            s, t, _, cores = cpu_reference_parallel(per_step, 100)
+            s, t, _, cores = cpu_reference_parallel(per_step, args.sims)
         else:
-            s, t, _, cores = cpu_reference_sims(per_step, 100)
+            s, t, _, cores = cpu_reference_sims(per_step, args.sims)
         tot_s += s
         tot_t += t
     v = tot_s / tot_t
-    sample = "%s; games from the start position, 100 sims/move, threads=1 schedule, %.0f s of simulations per step" % (
-        best["arrangement"], per_step)
+    sample = "%s; games from the start position, %d sims/move, threads=1 schedule, %.0f s of simulations per step" % (
+        best["arrangement"], args.sims, per_step)
     line = {"impl": "reference", "metric": "mcts_simulations_per_sec", "value": v, "unit": "simulations/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / max(1, args.steps) * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
