@@ -237,6 +237,8 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   {
     const char* g = getenv("CRL_NO_GRAPH");
     e->use_graph = !(g && g[0] == '1');
+    const char* pp = getenv("CRL_PERFT_PAIR");
+    e->perft_pair = !pp ? 0 : pp[0] == '5' ? 5 : pp[0] == '6' ? 6 : 0;
   }
   e->G = max_games;
   e->Kmax = max_inflight;
@@ -396,14 +398,17 @@ int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int
     const long long stride = e->perft_cap;
     // the root record goes to column 0 of buffer 0 (structure of arrays: word k at [k * stride])
     CRL_CUDA(cudaMemcpy2DAsync(e->perft_buf[0], (size_t)stride * 8, root_host, 8, 8, 9, cudaMemcpyHostToDevice, e->stream));
-    int rc = launch_perft_root(e, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk, min_frontier);
+    int rc = launch_perft_root(e, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk, min_frontier,
+                               e->perft_pair);
     if (rc) return rc;
     unsigned long long ctl[8];
     CRL_CUDA(cudaMemcpyAsync(ctl, e->perft_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e->stream));
     CRL_CUDA(cudaStreamSynchronize(e->stream));
     if (ctl[3] == 0) {
       *total_host = depth == 0 ? 1 : ctl[4];
-      if (lanes_host) *lanes_host = (int64_t)ctl[0];
+      // boards the walk ran on in lockstep: the stored frontier, or -- when the last two plies went through
+      // k_perft_pair -- the boards of the last-but-one ply it dealt to its lanes (ctl[5]; never stored)
+      if (lanes_host) *lanes_host = (int64_t)(ctl[5] ? ctl[5] : ctl[0]);
       if (bfs_plies_host) *bfs_plies_host = (int32_t)ctl[2];
       return CRL_OK;
     }

@@ -54,6 +54,9 @@ struct crl_engine_impl {
   u64* perft_buf[2] = {nullptr, nullptr};
   long long perft_cap = 0;
   unsigned long long* perft_ctl = nullptr;
+  int perft_pair = 0;                    // 0: expand the last-but-one ply into HBM, then walk it (default: measured
+                                         // faster); CRL_PERFT_PAIR=5 / 6: the last two plies in one pass (k_perft_pair,
+                                         // 96- / 80-register build)
   // pinned staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
@@ -114,7 +117,7 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
 int launch_frontier(crl_engine_impl* e, const u64* boards, int n, const long long* offsets, u64* out,
                     long long out_n, int* counts);
 int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl, int depth, int bulk,
-                      long long min_frontier);
+                      long long min_frontier, int pair);
 int launch_encode_boards(crl_engine_impl* e, const u64* boards, const u64* hist, const u8* hist_len, int n,
                          __nv_bfloat16* planes);
 int launch_policy_index(crl_engine_impl* e, const u16* moves, const int* counts, int n, int16_t* idx);

@@ -163,9 +163,12 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ b
 // Frontiers ping-pong between buf[0] and buf[1] (SoA with stride `cap`); the current one is buf[ctl[2] & 1].
 // does the next ply still expand breadth-first?  Yes while the frontier is small, or while the remaining depth is
 // more than one lane's stack can walk; never beyond depth-1 plies (the last ply is always counted by the walk).
-__device__ __forceinline__ bool bfs_active(const unsigned long long* ctl, long long min_frontier, int depth) {
+// With `pair` the last TWO plies belong to k_perft_pair (the last-but-one ply is expanded and counted in one pass,
+// never stored), so breadth-first expansion stops one ply earlier.
+__device__ __forceinline__ bool bfs_active(const unsigned long long* ctl, long long min_frontier, int depth, int pair) {
   const int plies = (int)ctl[2];
-  if (ctl[3] || plies >= depth - 1) return false;
+  const int last = (pair && depth >= 2) ? depth - 2 : depth - 1;
+  if (ctl[3] || plies >= last) return false;
   return (long long)ctl[0] < min_frontier || depth - plies > PERFT_MAX_DEPTH;
 }
 
@@ -204,11 +207,11 @@ struct BfsSink {
 
 __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
                                                          unsigned long long* __restrict__ ctl, long long min_frontier,
-                                                         int depth) {
+                                                         int depth, int pair) {
   __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
   __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
   __shared__ int s_pre[RULES_BLOCK / 32][33];
-  if (!bfs_active(ctl, min_frontier, depth)) return;                  // uniform for the whole grid
+  if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid
   const long long n = (long long)ctl[0];
   const int plies = (int)ctl[2];
   const u64* in = (plies & 1) ? buf1 : buf0;
@@ -275,26 +278,141 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0,
     __syncwarp();                                                      // the rows are reused by the next round
   }
 }
-__global__ void k_bfs_commit(unsigned long long* __restrict__ ctl, long long min_frontier, int depth) {
-  if (!bfs_active(ctl, min_frontier, depth)) return;
+__global__ void k_bfs_commit(unsigned long long* __restrict__ ctl, long long min_frontier, int depth, int pair) {
+  if (!bfs_active(ctl, min_frontier, depth, pair)) return;
   ctl[0] = ctl[1];
   ctl[1] = 0;
   ctl[2] += 1;
 }
 __global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
                                                             long long cap, unsigned long long* __restrict__ ctl, int depth,
-                                                            int bulk) {
+                                                            int bulk, int pair) {
   if (ctl[3]) return;
   const long long n = (long long)ctl[0];
   const int plies = (int)ctl[2];
   const u64* in = (plies & 1) ? buf1 : buf0;
   const int remaining = depth - plies;
+  if (pair && remaining == 2) return;                                  // k_perft_pair counts these
   unsigned long long mine = 0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     mine += remaining <= 0 ? 1ull : perft_lane(load_soa(in, cap, i), remaining, bulk);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&ctl[4], mine);
+}
+
+// OPTIONAL (CRL_PERFT_PAIR=5 / 6; off by default -- measured, it does not pay: profiles/r01_perft_pair_probe.json).
+// The last two plies in one pass, nothing stored: when the frontier sits two plies above the leaves, a warp takes P of
+// its boards per round (P = 32 for a large frontier, fewer for a small one so that every SM still gets warps), lanes
+// 0..P-1 generate their board's moves into shared-memory rows exactly as k_bfs_ply does, and the warp's children are
+// dealt round-robin to all 32 lanes, which make the move in registers and COUNT the child's legal moves (bulk) or
+// generate and make each of them (every leaf made).  Against "expand the last-but-one ply, then walk it" this drops
+// the 72-byte store and the 72-byte load of every board of the largest frontier (Kiwipete depth 5: 4.1 M boards =
+// 588 MB; start depth 7: 119 M boards = 17 GB) and one ply + commit launch pair, while every lane still does one
+// make + one generation per step, so warps stay converged.   ctl[5] = boards dealt (the lockstep lanes of the walk).
+// Result on B200: bit-identical totals, but 0-8 % SLOWER with leaf bulk counting and 5-15 % slower making every leaf
+// (Kiwipete d5 0.68 -> 0.71 ms, start d7 11.6 -> 11.7 ms at 96 registers; worse at 80): the stored ply's HBM traffic
+// was already hidden behind the integer pipe, and the fused kernel runs at 20 warps per SM where the walk runs at 28.
+template <int BULK>
+__device__ __forceinline__ unsigned long long pair_leaf(const Board& c) {
+  if (BULK) {
+    CountSink cs{0};
+    generate_legal(c, cs);
+    return (unsigned long long)cs.n;
+  }
+  u16 local[MAX_MOVES];
+  StoreSink ss{local, 0};
+  generate_legal(c, ss);
+  unsigned long long t = 0;
+  for (int k = 0; k < ss.n; ++k) {
+    Board d = c;
+    make_move(d, local[k]);
+    t += (d.bb[KING] != 0);
+  }
+  return t;
+}
+
+// MINB = resident blocks per SM the register allocation aims at: 5 -> 96 registers, no spills, 20 warps per SM;
+// 6 -> 80 registers, ~130 bytes of spills, 24 warps per SM (CRL_PERFT_PAIR=5 / 6 picks; see scripts/perft_pair_probe.py)
+template <int BULK, int MINB>
+__global__ void __launch_bounds__(RULES_BLOCK, MINB) k_perft_pair(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
+                                                            long long cap, unsigned long long* __restrict__ ctl, int depth) {
+  __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
+  __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
+  __shared__ int s_pre[RULES_BLOCK / 32][33];
+  if (ctl[3]) return;
+  const long long n = (long long)ctl[0];
+  const int plies = (int)ctl[2];
+  if (depth - plies != 2) return;                                      // uniform for the whole grid
+  const u64* in = (plies & 1) ? buf1 : buf0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long n_warps = (long long)gridDim.x * (RULES_BLOCK / 32);
+  // boards per warp and round: 32 when that still leaves >= 32 warp-rounds per SM, else fewer (phase 1 then runs on
+  // P of the 32 lanes, but every SM gets work: Kiwipete depth 5 deals 97,862 boards as 6,116 rounds of 16)
+  const long long target = n_warps < 148 * 32 ? n_warps : 148 * 32;
+  int P = 32;
+  while (P > 1 && n < (long long)P * target) P >>= 1;
+  unsigned long long mine = 0, dealt = 0;
+  for (long long r = (long long)blockIdx.x * (RULES_BLOCK / 32) + warp; r * P < n; r += n_warps) {
+    // ---- phase 1: lanes 0..P-1 take one board each ----
+    const long long i = r * P + lane;
+    u16 spill[MAX_MOVES - BFS_CAP];
+    BfsSink sink{s_moves[warp][lane], spill, 0};
+    if (lane < P && i < n) {
+      const Board b = load_soa(in, cap, i);
+      generate_legal(b, sink);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s_board[warp][k][lane] = b.bb[k];
+      s_board[warp][8][lane] = b.meta;
+    }
+    int pre = sink.n;                                                  // inclusive prefix sum over the warp
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, pre, off);
+      if (lane >= off) pre += v;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, pre, 31);
+    s_pre[warp][lane] = pre - sink.n;
+    if (lane == 31) s_pre[warp][32] = warp_total;
+    __syncwarp();
+    if (lane == 0) dealt += (unsigned long long)warp_total;
+    // ---- phase 2: children dealt round-robin, made and counted in registers ----
+    for (int j = lane; j < warp_total; j += 32) {
+      int lo = 0, hi = 32;
+#pragma unroll
+      for (int step = 0; step < 5; ++step) {
+        const int mid = (lo + hi) >> 1;
+        if (s_pre[warp][mid] <= j) lo = mid;
+        else hi = mid;
+      }
+      const int k = j - s_pre[warp][lo];
+      if (k >= BFS_CAP) continue;                                      // stays with its board's lane (phase 3)
+      Board c;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) c.bb[w] = s_board[warp][w][lo];
+      c.meta = s_board[warp][8][lo];
+      make_move(c, s_moves[warp][lo][k]);
+      mine += pair_leaf<BULK>(c);
+    }
+    // ---- phase 3: boards with more than BFS_CAP moves finish their own list ----
+    if (sink.n > BFS_CAP) {                                            // (the board is re-read from its parked copy:
+      for (int k = BFS_CAP; k < sink.n; ++k) {                         //  keeping it in registers across phase 2 costs occupancy)
+        Board c;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) c.bb[w] = s_board[warp][w][lane];
+        c.meta = s_board[warp][8][lane];
+        make_move(c, spill[k - BFS_CAP]);
+        mine += pair_leaf<BULK>(c);
+      }
+    }
+    __syncwarp();                                                      // the rows are reused by the next round
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if (lane == 0) {
+    if (mine) atomicAdd(&ctl[4], mine);
+    if (dealt) atomicAdd(&ctl[5], dealt);
+  }
 }
 
 // ---- one breadth-first ply ----------------------------------------------------------------------------
@@ -351,7 +469,7 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
 }
 // enqueues the whole device-driven perft of the root record already stored at buf0[k*cap] (k = 0..8); ctl is zeroed here
 int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl, int depth, int bulk,
-                      long long min_frontier) {
+                      long long min_frontier, int pair) {
   if (depth < 0 || depth > 64) {
     set_error("crl_perft_root_host: depth %d is not supported", depth);
     return CRL_EINVAL;
@@ -359,7 +477,8 @@ int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, u
   CRL_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), e->stream));
   const unsigned long long one = 1;
   CRL_CUDA(cudaMemcpyAsync(ctl, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
-  const int max_plies = depth - 1 > 0 ? depth - 1 : 0;
+  if (depth < 2) pair = 0;
+  const int max_plies = depth - 1 - (pair ? 1 : 0) > 0 ? depth - 1 - (pair ? 1 : 0) : 0;
   const int max_grid = 148 * 12;
   long long bound = 1;
   for (int ply = 0; ply < max_plies; ++ply) {
@@ -367,15 +486,27 @@ int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, u
     const int grid = (int)(div_up(bound, RULES_BLOCK) < max_grid ? div_up(bound, RULES_BLOCK) : max_grid);
     {
       LaunchScope ls(e, KC_MOVEGEN, 2);
-      k_bfs_ply<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth);
-      k_bfs_commit<<<1, 1, 0, e->stream>>>(ctl, min_frontier, depth);
+      k_bfs_ply<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair);
+      k_bfs_commit<<<1, 1, 0, e->stream>>>(ctl, min_frontier, depth, pair);
       CRL_CUDA(cudaGetLastError());
     }
     bound = bound * 218 < cap ? bound * 218 : cap;
   }
-  LaunchScope ls(e, KC_MOVEGEN);
+  LaunchScope ls(e, KC_MOVEGEN, pair ? 2 : 1);
   const int grid = (int)(div_up(bound, RULES_BLOCK) < max_grid * 4 ? div_up(bound, RULES_BLOCK) : max_grid * 4);
-  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk);
+  if (pair) {
+    // one warp per board while the frontier is small (the kernel picks the boards per warp from the real count)
+    const long long want = div_up(bound, (long long)(RULES_BLOCK / 32));
+    const int pgrid = (int)(want < 148 * 16 ? want : 148 * 16);        // 9,472 warps: two per resident warp slot
+    if (pair == 5) {
+      if (bulk) k_perft_pair<1, 5><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
+      else k_perft_pair<0, 5><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
+    } else {
+      if (bulk) k_perft_pair<1, 6><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
+      else k_perft_pair<0, 6><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
+    }
+  }
+  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk, pair);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

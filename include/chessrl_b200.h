@@ -84,7 +84,11 @@ int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int b
 /* perft of ONE position in one call, no host round trip between plies: breadth-first plies on the device (children
  * placed with warp-aggregated atomics, arbitrary order) until the frontier holds >= min_frontier boards, then one
  * depth-first walk per lane (bulk as in crl_perft).  root_host [9] (AoS record).  Outputs: *total_host = perft(depth);
- * optional *lanes_host = boards in the final frontier, *bfs_plies_host = plies expanded breadth-first.
+ * Experimental, off by default (measured slower): CRL_PERFT_PAIR=5 or 6 in the environment at crl_create time runs the
+ * last two plies as ONE pass when the stored frontier sits two plies above the leaves (each board's children are dealt
+ * to the lanes of a warp, made in registers and counted; the last-but-one ply is never stored).
+ * optional *lanes_host = boards the walk ran on in lockstep (the stored frontier, or the boards of the last-but-one ply
+ * when the two-ply pass ran), *bfs_plies_host = plies expanded breadth-first into HBM.
  * The frontier buffers are owned by the engine and grow on demand (CRL_ENOMEM if they cannot). */
 int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier,
                         uint64_t* total_host, int64_t* lanes_host, int32_t* bfs_plies_host);

@@ -16,6 +16,7 @@ from chessrl_b200 import boards as B
 pytestmark = pytest.mark.gpu
 chess = O.chess
 
+PAIR = os.environ.get("CRL_PERFT_PAIR", "0") in ("5", "6")     # the last two plies as one pass (k_perft_pair; optional)
 KIWI = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
 PERFT5 = {B.STARTING_FEN: [20, 400, 8902, 197281, 4865609], KIWI: [48, 2039, 97862, 4085603, 193690690]}
 EXTRA = {
@@ -200,8 +201,10 @@ def test_perft_root_device_driven(engine1, fen, expected):
             total, lanes, plies = engine1.perft_root(rec, depth, bulk=bulk, min_frontier=min_frontier)
             assert total == want, (fen, depth, min_frontier, bulk, total, want)
             assert 0 <= plies <= depth - 1 and lanes >= 1
-            if min_frontier == 1:
-                assert plies == 0 and lanes == 1
+            if min_frontier == 1:                 # nothing expanded into HBM; depth 2 = the two-ply pass on the root itself
+                assert plies == 0 and lanes == (expected[0] if depth == 2 and PAIR else 1)
+            elif depth >= 2 and PAIR and min_frontier == 1 << 20:
+                assert plies == depth - 2 and lanes == expected[depth - 2]     # last-but-one ply dealt, never stored
     assert engine1.perft_root(rec, 0)[0] == 1
 
 
@@ -265,3 +268,23 @@ def test_rules_on_unreachable_random_positions(engine1):
             b.pop()
             k += 1
     assert k == kids.shape[1]
+
+
+@pytest.mark.parametrize("mode", ["5", "6"])
+def test_perft_root_two_ply_pass(mode, monkeypatch):
+    """The optional fused pass over the last two plies (CRL_PERFT_PAIR=5 / 6, read at engine creation): same totals as
+    the default path for every depth and frontier target; the last-but-one ply is dealt to the lanes but never stored."""
+    from chessrl_b200.engine import Engine
+    monkeypatch.setenv("CRL_PERFT_PAIR", mode)
+    e = Engine(max_games=1, max_nodes=8)
+    for fen, exp in list(PERFT5.items()) + perft_kats.EDGE[:4] + perft_kats.EDGE[6:9]:
+        rec = B.record_from_fen(fen)
+        for depth, want in enumerate(exp, start=1):
+            for min_frontier, bulk in ((1, True), (300, False), (1 << 20, True)):
+                if (not bulk and want > 5_000_000) or (min_frontier == 1 and want > 200_000):
+                    continue
+                total, lanes, plies = e.perft_root(rec, depth, bulk=bulk, min_frontier=min_frontier)
+                assert total == want, (fen, depth, min_frontier, bulk, total, want)
+                if depth >= 2 and min_frontier == 1 << 20:
+                    assert plies == depth - 2 and lanes == exp[depth - 2]
+    e.close()
