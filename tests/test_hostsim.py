@@ -211,6 +211,45 @@ def test_device_tree_core_wave_mode_matches_reference(lib, golden_dir):
                 assert lib.hs_edge_score(V[k], W[k], Pr[k], Rs[k]) == float.fromhex(kid["score"])
 
 
+def test_device_core_results_along_playouts_from_unreachable_positions(lib):
+    """80 seeded playouts (<= 90 plies, mostly quiet moves) from position_fuzz positions, a third of them started a
+    few plies before the fifty-move claim: legal list, FEN, transposition-key repetitions and Game.get_result
+    (game.py:92-109: claim, mate, stalemate, insufficient material) ply by ply against the restatement."""
+    import random
+    rng = random.Random(31)
+    plies, ends, fifty = 0, {}, 0
+    for gi in range(80):
+        fen, ob = position_fuzz.random_fen(rng)
+        if gi % 3 == 0:
+            parts = fen.split()
+            parts[4] = str(rng.randrange(80, 100))
+            fen = " ".join(parts)
+            ob = chess.Board(fen)
+        rec, keys = B.record_from_fen(fen), []
+        for i in range(90):
+            legal = [m.uci() for m in ob.generate_legal_moves()]
+            ml, chk, epl = movegen(lib, rec)
+            assert ml == legal, (fen, i)
+            assert B.fen_from_record(rec, epl) == ob.fen(), (fen, i)
+            k = lib.hs_key(rec.ctypes.data_as(u64p), epl)
+            rev = B.meta_fields(rec[8])["rev"]
+            reps = sum(1 for j in range(1, rev + 1) if len(keys) - j >= 0 and keys[len(keys) - j] == k)
+            keys.append(k)
+            res = lib.hs_result(rec.ctypes.data_as(u64p), len(ml), chk, reps)
+            want = O.OGame(board=ob).get_result()
+            assert (None if res == 2 else res) == want, (fen, i, res, want)
+            if want is not None:
+                ends[want] = ends.get(want, 0) + 1
+                fifty += ob.halfmove_clock >= 100
+                break
+            quiet = [m for m in legal if not ob.is_zeroing(chess.Move.from_uci(m))]
+            m = rng.choice(quiet if quiet and rng.random() < 0.85 else legal)
+            lib.hs_make(rec.ctypes.data_as(u64p), B.uci_to_move(m))
+            ob.push(chess.Move.from_uci(m))
+            plies += 1
+    assert plies > 4000 and ends.get(0, 0) >= 10 and ends.get(1, 0) + ends.get(-1, 0) >= 5 and fifty >= 8, (plies, ends, fifty)
+
+
 def test_device_tree_core_from_unreachable_roots(lib):
     """Searches rooted at position_fuzz positions (terminal children, promotions, ep and castling inside the tree,
     up to 90 legal moves at the root): visit counts, value sums, results and (move, reply) lines against the
