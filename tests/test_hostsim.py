@@ -288,6 +288,44 @@ def test_device_tree_core_from_unreachable_roots(lib):
     assert searched >= 50 and terminal_kids >= 3
 
 
+def test_device_tree_core_wave_mode_from_unreachable_roots(lib):
+    """threads=K (wave schedule, virtual loss) rooted at position_fuzz positions: visit counts, value sums, results,
+    lines and the NUMBER OF WAVES against the restated SelfPlayTree(threads=K)."""
+    import random
+    tab = _label_table()
+    t = lib.hs_tree_new(1024, 1024 * 220, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    rng = random.Random(23)
+    searched = cut = 0
+    for _ in range(48):
+        fen, _b = position_fuzz.random_fen(rng)
+        sims, K = rng.choice([7, 40, 96]), rng.choice([2, 3, 6, 16, 64])
+        seed, bits = rng.randrange(1, 1000), rng.choice([3, 11, 24])
+        g = O.OGame(board=chess.Board(fen))
+        if g.get_result() is not None:
+            continue
+        rec = B.record_from_fen(fen)
+        none = np.zeros(1, dtype=np.uint16)
+        assert lib.hs_game_set(t, rec.ctypes.data_as(u64p), none.ctypes.data_as(u16p), 0) == 0
+        w = lib.hs_search_wave(t, sims, K, seed, bits)
+        ot = O.OSelfPlayTree(g, threads=K)
+        ot.search_move(O.OAgent(O.hash_evaluator(seed, bits)), max_iters=sims, noise=False)
+        assert w >> 24 == 0 and (w & 0xFFFFFF) == ot.n_waves, (fen, K, sims, w, ot.n_waves)
+        cut += ot.n_waves > -(-sims // K)
+        V, W, Pr = (ctypes.c_int * 256)(), (ctypes.c_double * 256)(), (ctypes.c_float * 256)()
+        M, R, Rs = (ctypes.c_uint16 * 256)(), (ctypes.c_uint16 * 256)(), (ctypes.c_int * 256)()
+        rv, rw = ctypes.c_int(), ctypes.c_double()
+        n = lib.hs_root_stats(t, V, W, Pr, M, R, Rs, ctypes.byref(rv), ctypes.byref(rw))
+        kids = ot.root.children
+        assert n == len(kids) and rv.value == ot.root.visits and rw.value == float(ot.root.value), (fen, K)
+        for k, c in enumerate(kids):
+            assert V[k] == c.visits and W[k] == float(c.value), (fen, K, k)
+            assert (None if Rs[k] == 2 else Rs[k]) == c.state.get_result(), (fen, K, k)
+            line = [B.move_to_uci(M[k])] + ([B.move_to_uci(R[k])] if R[k] != 0xFFFF else [])
+            assert line == [str(x) for x in c.state.board.move_stack], (fen, K, k)
+        searched += 1
+    assert searched >= 40 and cut >= 3
+
+
 def test_device_history_walk_matches_planes(lib):
     """The parent-chain walk used for history planes inside the tree reproduces the move-stack walk of
     netencoder._get_game_history for a node deep in a search."""
