@@ -1,0 +1,1 @@
+"""Small host-side utilities (logger)."""
