@@ -202,15 +202,50 @@ CRL_HD u64 attackers_of(const Board& b, int sq, u64 occ, int by_white) {
   return a & b.bb[by_white ? OCC_W : OCC_B];
 }
 
+// ---- set-wise slider attacks: Kogge-Stone occluded fills --------------------------------------------
+// All sliders of a set at once, one direction at a time: three doubling steps flood `gen` through the empty squares
+// `pro`, one more single step lands on the first blocker.  No loop over pieces, so the lanes of a warp (which hold
+// different numbers of sliders) never diverge, and within ONE direction every square is reached by at most one ray
+// (from the nearest slider behind it) -- so popcounts per direction add up to the sliders' move count.
+template <int DIR>   // 0 N, 1 S, 2 E, 3 W, 4 NE, 5 NW, 6 SE, 7 SW
+CRL_HD u64 ray_attacks_set(u64 gen, u64 empty) {
+  constexpr bool up = DIR == 0 || DIR == 2 || DIR == 4 || DIR == 5;                 // towards higher square numbers
+  constexpr int sh = DIR <= 1 ? 8 : DIR <= 3 ? 1 : (DIR == 4 || DIR == 7) ? 9 : 7;
+  constexpr u64 wrap = (DIR == 2 || DIR == 4 || DIR == 6) ? ~FILE_A : (DIR == 3 || DIR == 5 || DIR == 7) ? ~FILE_H : ~0ULL;
+  u64 pro = empty & wrap;
+  if (up) {
+    gen |= pro & (gen << sh);
+    pro &= pro << sh;
+    gen |= pro & (gen << (2 * sh));
+    pro &= pro << (2 * sh);
+    gen |= pro & (gen << (4 * sh));
+    return (gen << sh) & wrap;
+  }
+  gen |= pro & (gen >> sh);
+  pro &= pro >> sh;
+  gen |= pro & (gen >> (2 * sh));
+  pro &= pro >> (2 * sh);
+  gen |= pro & (gen >> (4 * sh));
+  return (gen >> sh) & wrap;
+}
+// union of the attacks of rook-like / bishop-like sliders under occupancy `occ`
+CRL_HD u64 rook_attacks_set(u64 rq, u64 occ) {
+  const u64 e = ~occ;
+  return ray_attacks_set<0>(rq, e) | ray_attacks_set<1>(rq, e) | ray_attacks_set<2>(rq, e) | ray_attacks_set<3>(rq, e);
+}
+CRL_HD u64 bishop_attacks_set(u64 bq, u64 occ) {
+  const u64 e = ~occ;
+  return ray_attacks_set<4>(bq, e) | ray_attacks_set<5>(bq, e) | ray_attacks_set<6>(bq, e) | ray_attacks_set<7>(bq, e);
+}
+
 // every square attacked by colour `by_white` under occupancy `occ`
 CRL_HD u64 attack_map(const Board& b, u64 occ, int by_white) {
   u64 side = b.bb[by_white ? OCC_W : OCC_B];
   u64 a = pawn_attacks_set(b.bb[PAWN] & side, by_white) | knight_attacks_set(b.bb[KNIGHT] & side) |
           king_attacks_set(b.bb[KING] & side);
-  u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & side;
-  while (rq) a |= rook_attacks(pop_msb(rq), occ);
-  u64 bq = (b.bb[BISHOP] | b.bb[QUEEN]) & side;
-  while (bq) a |= bishop_attacks(pop_msb(bq), occ);
+  const u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & side, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & side;
+  if (rq) a |= rook_attacks_set(rq, occ);
+  if (bq) a |= bishop_attacks_set(bq, occ);
   return a;
 }
 
@@ -328,6 +363,30 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   // (1) officers (and, when not in check, the king), source squares h8 -> a1
   u64 officers = us & ~b.bb[PAWN];
   if (checkers) officers &= ~kbit;
+  if (Sink::kCounting) {
+    // counting only: every unpinned officer set-wise.  Within one direction a square is reached by at most one ray /
+    // one knight jump, so the popcounts per direction add up to the number of moves; no loop over pieces, no
+    // divergence between lanes holding different material.  Pinned officers (rare) keep the per-piece path below.
+    const u64 ok = ~us & target;
+    if (!checkers) sink.add(popc64(king_targets & ~danger));
+    const u64 free_o = officers & ~pinned & ~kbit;
+    const u64 n = b.bb[KNIGHT] & free_o;
+    if (n) {
+      const u64 l1 = (n >> 1) & ~FILE_H, l2 = (n >> 2) & ~(FILE_G | FILE_H);
+      const u64 r1 = (n << 1) & ~FILE_A, r2 = (n << 2) & ~(FILE_A | FILE_B);
+      sink.add(popc64((l1 << 16) & ok) + popc64((l1 >> 16) & ok) + popc64((r1 << 16) & ok) + popc64((r1 >> 16) & ok) +
+               popc64((l2 << 8) & ok) + popc64((l2 >> 8) & ok) + popc64((r2 << 8) & ok) + popc64((r2 >> 8) & ok));
+    }
+    const u64 empty = ~occ;
+    const u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & free_o, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & free_o;
+    if (rq)
+      sink.add(popc64(ray_attacks_set<0>(rq, empty) & ok) + popc64(ray_attacks_set<1>(rq, empty) & ok) +
+               popc64(ray_attacks_set<2>(rq, empty) & ok) + popc64(ray_attacks_set<3>(rq, empty) & ok));
+    if (bq)
+      sink.add(popc64(ray_attacks_set<4>(bq, empty) & ok) + popc64(ray_attacks_set<5>(bq, empty) & ok) +
+               popc64(ray_attacks_set<6>(bq, empty) & ok) + popc64(ray_attacks_set<7>(bq, empty) & ok));
+    officers &= pinned & ~b.bb[KNIGHT];            // a pinned knight never moves; pinned sliders one by one
+  }
   while (officers) {
     const int from = pop_msb(officers);
     const u64 fb = bit(from);

@@ -100,6 +100,7 @@ def test_device_core_on_unreachable_random_positions(lib):
         assert got == want, fen
         assert bool(chk) == b.is_check() and bool(epl) == b.has_legal_en_passant(), fen
         assert B.fen_from_record(rec, epl) == b.fen(), fen
+        assert lib.hs_perft(rec.ctypes.data_as(u64p), 1, 1) == len(want), fen          # set-wise counting path
         seen["ep"] += bool(epl)
         seen["check"] += bool(chk)
         for m in want:
@@ -112,6 +113,7 @@ def test_device_core_on_unreachable_random_positions(lib):
             ml2, _, epl2 = movegen(lib, child)
             assert B.fen_from_record(child, epl2) == b.fen(), (fen, m)
             assert len(ml2) == sum(1 for _ in b.generate_legal_moves()), (fen, m)
+            assert lib.hs_perft(child.ctypes.data_as(u64p), 1, 1) == len(ml2), (fen, m)
             b.pop()
         seen["moves"] += len(want)
     assert seen["ep"] > 50 and seen["check"] > 200 and seen["castle"] > 50 and seen["promo"] > 200, seen
