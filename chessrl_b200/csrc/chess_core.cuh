@@ -314,7 +314,24 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   const u64 kbit = bit(ksq);
   constexpr int base = white ? 0 : 56;
 
-  const u64 checkers = attackers_of(b, ksq, occ, !white);
+  // Board.checkers_mask() and the absolute pins (Board._slider_blockers) from ONE walk over the enemy sliders that
+  // stand on a line with the king (found without occupancy): nothing in between = a checker, exactly one piece in
+  // between = that piece is pinned if it is ours.  Step attackers (knight, pawn, the enemy king python-chess also
+  // counts) are set-wise.  This replaces four hyperbola-quintessence line scans from the king's square.
+  u64 checkers = ((knight_attacks_set(kbit) & b.bb[KNIGHT]) | (pawn_attacks_set(kbit, white) & b.bb[PAWN]) |
+                  (king_attacks_set(kbit) & b.bb[KING])) & them;
+  u64 pinned = 0;
+  {
+    u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & them, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & them;
+    u64 snipers = ((rank_mask(ksq) | file_mask(ksq)) & rq) | ((diag_mask(ksq) | anti_mask(ksq)) & bq);
+    while (snipers) {
+      const int s = pop_msb(snipers);
+      const u64 mid = between(ksq, s) & occ;
+      if (!mid) checkers |= bit(s);
+      else if (!(mid & (mid - 1))) pinned |= mid;
+    }
+    pinned &= us;
+  }
   info.in_check = checkers != 0;
 
   // squares whose safety matters: the king's destinations and the castling paths that are otherwise clear.
@@ -329,19 +346,6 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   }
   u64 danger = 0;
   if (king_targets || castle_k || castle_q) danger = attack_map(b, occ ^ kbit, !white);   // king may not step here
-
-  // absolute pins (Board._slider_blockers): enemy sliders on a line with the king (no occupancy needed for that)
-  u64 pinned = 0;
-  {
-    u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & them, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & them;
-    u64 snipers = ((rank_mask(ksq) | file_mask(ksq)) & rq) | ((diag_mask(ksq) | anti_mask(ksq)) & bq);
-    while (snipers) {
-      const int s = pop_msb(snipers);
-      u64 mid = between(ksq, s) & occ;
-      if (mid && !(mid & (mid - 1))) pinned |= mid;
-    }
-    pinned &= us;
-  }
 
   // evasion target mask for non-king pieces
   u64 target = ~0ULL;
