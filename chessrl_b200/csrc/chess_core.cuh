@@ -166,6 +166,18 @@ CRL_HD u64 king_attacks_set(u64 b) {
   u64 c = b | a;
   return a | (c << 8) | (c >> 8);
 }
+// step attacks of ONE square: the pattern around c3 / b2 slid to the square, wrap-around files cut off
+// (a third of the instructions of the set-wise forms above, which have to shift in every direction)
+CRL_HD u64 knight_attacks_sq(int sq) {
+  constexpr u64 span = 0x0000000A1100110AULL;                            // knight on c3 (18)
+  const u64 a = sq >= 18 ? span << (sq - 18) : span >> (18 - sq);
+  return a & ((sq & 7) < 4 ? ~(FILE_G | FILE_H) : ~(FILE_A | FILE_B));
+}
+CRL_HD u64 king_attacks_sq(int sq) {
+  constexpr u64 span = 0x0000000000070507ULL;                            // king on b2 (9)
+  const u64 a = sq >= 9 ? span << (sq - 9) : span >> (9 - sq);
+  return a & ((sq & 7) < 4 ? ~FILE_H : ~FILE_A);
+}
 CRL_HD u64 pawn_attacks_set(u64 b, int white) {
   return white ? (((b << 9) & ~FILE_A) | ((b << 7) & ~FILE_H)) : (((b >> 7) & ~FILE_A) | ((b >> 9) & ~FILE_H));
 }
@@ -293,7 +305,7 @@ CRL_HD bool ep_capture_safe(const Board& b, int from, int ep, int white, int ksq
   if (rook_attacks(ksq, occ) & rq) return false;
   if (bishop_attacks(ksq, occ) & bq) return false;
   u64 k = bit(ksq);
-  if (knight_attacks_set(k) & b.bb[KNIGHT] & them) return false;
+  if (knight_attacks_sq(ksq) & b.bb[KNIGHT] & them) return false;
   if (pawn_attacks_set(k, white) & b.bb[PAWN] & them) return false;
   return true;
 }
@@ -318,8 +330,9 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   // stand on a line with the king (found without occupancy): nothing in between = a checker, exactly one piece in
   // between = that piece is pinned if it is ours.  Step attackers (knight, pawn, the enemy king python-chess also
   // counts) are set-wise.  This replaces four hyperbola-quintessence line scans from the king's square.
-  u64 checkers = ((knight_attacks_set(kbit) & b.bb[KNIGHT]) | (pawn_attacks_set(kbit, white) & b.bb[PAWN]) |
-                  (king_attacks_set(kbit) & b.bb[KING])) & them;
+  const u64 king_ring = king_attacks_sq(ksq);
+  u64 checkers = ((knight_attacks_sq(ksq) & b.bb[KNIGHT]) | (pawn_attacks_set(kbit, white) & b.bb[PAWN]) |
+                  (king_ring & b.bb[KING])) & them;
   u64 pinned = 0;
   {
     u64 rq = (b.bb[ROOK] | b.bb[QUEEN]) & them, bq = (b.bb[BISHOP] | b.bb[QUEEN]) & them;
@@ -337,7 +350,7 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
   // squares whose safety matters: the king's destinations and the castling paths that are otherwise clear.
   // The enemy attack map (the most expensive part of the generator) is skipped when there are none -- a king
   // boxed in by its own pieces, as in most opening positions.
-  const u64 king_targets = king_attacks_set(kbit) & ~us;
+  const u64 king_targets = king_ring & ~us;
   const int rights = meta_castle(b.meta) >> (white ? 0 : 2);
   bool castle_k = false, castle_q = false;
   if (!checkers && ksq == base + 4) {
@@ -395,7 +408,7 @@ CRL_HD GenInfo generate_legal_side(const Board& b, Sink& sink) {
     const int from = pop_msb(officers);
     const u64 fb = bit(from);
     u64 t;
-    if (fb & b.bb[KNIGHT]) t = knight_attacks_set(fb);
+    if (fb & b.bb[KNIGHT]) t = knight_attacks_sq(from);
     else if (fb & b.bb[KING]) t = king_targets & ~danger;
     else {
       t = 0;
