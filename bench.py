@@ -268,8 +268,8 @@ def kernel_rooflines(engine, peaks, flush, net_loaded):
     ms = _time_launch(lambda: check(engine.lib.crl_movegen(engine.h, _ptr(boards), n, _ptr(moves), _ptr(counts), None)), flush)
     avg_l = float(counts.float().mean().item())
     byt = n * (72 + 2 * avg_l + 4)
-    out["movegen"] = {"bound": "INT32 ALU pipe (64-bit bitboard logic on the half-rate integer pipe; ncu: pipe_alu 71.7 % of peak, "
-                               "profiles/r01_ncu_rules_kernels_after_opt.txt), then hbm", "boards": n, "avg_legal_moves": avg_l, "us": ms * 1e3,
+    out["movegen"] = {"bound": "INT32 ALU pipe (64-bit bitboard logic on the half-rate integer pipe; ncu before the set-wise rule core: pipe_alu "
+                               "71.7 % of peak, profiles/r01_ncu_rules_kernels_after_opt.txt), then hbm", "boards": n, "avg_legal_moves": avg_l, "us": ms * 1e3,
                       "boards_per_s": n / ms * 1e3, "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s",
                       "frac": byt / ms / 1e6 / hbm, "algorithmic_bytes_per_board": 72 + 2 * avg_l + 4}
     first = moves[:, 0].contiguous()
