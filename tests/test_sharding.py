@@ -27,14 +27,15 @@ WORKER = textwrap.dedent("""
     out = {"rank": rank, "range": [lo, hi], "same": bool(same), "perft_total": total}
     if rank == 0:
         out["gathered"] = [[list(map(int, mv)), res, col] for mv, res, col in got]
-    print("RESULT" + json.dumps(out))
+    with open(os.path.join(%r, "rank%%d.json" %% rank), "w") as f:    # one file per rank: stdout of two ranks interleaves
+        json.dump(out, f)
     dist.destroy_process_group()
 """)
 
 
 def test_gloo_world2(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % ROOT)
+    script.write_text(WORKER % (ROOT, str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)]
@@ -42,10 +43,10 @@ def test_gloo_world2(tmp_path):
     assert p.returncode == 0, p.stderr[-2000:]
     import json
     res = {}
-    for line in p.stdout.splitlines():
-        if "RESULT" in line:
-            r = json.loads(line[line.index("RESULT") + 6:])
-            res[r["rank"]] = r
+    for rank in (0, 1):
+        with open(tmp_path / ("rank%d.json" % rank)) as f:
+            res[rank] = json.load(f)
+        assert res[rank]["rank"] == rank
     assert res[0]["range"] == [0, 6] and res[1]["range"] == [6, 11]
     assert res[0]["same"] and res[1]["same"]
     import numpy as np
