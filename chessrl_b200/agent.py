@@ -27,14 +27,12 @@ class Agent(AgentDistributed):
         from . import training
         training.train(self.model, dataset, epochs=epochs, logdir=logdir, batch_size=batch_size,
                        validation_split=validation_split)
-        self.model.version = getattr(self.model, "version", 0) + 1
 
     def save(self, path):
         self.model.save_weights(path)
 
     def load(self, path):
         self.model.load_weights(path)
-        self.model.version = getattr(self.model, "version", 0) + 1
 
     def get_copy(self):
         return self

@@ -42,8 +42,9 @@ class AgentDistributed(Player):
         self._hash_eval = (int(seed), int(policy_bits))
 
     def _model_obj(self):
-        if self._model is None:
-            self._model = _ENDPOINT_MODELS.get(self.address)
+        if self.address is not None and self.address in _ENDPOINT_MODELS:
+            # re-resolved on every use: PredictWorker.reload_model may have registered a new model for the endpoint
+            self._model = _ENDPOINT_MODELS[self.address]
         if self._model is None:
             from .model import ChessModel
             self._model = ChessModel()

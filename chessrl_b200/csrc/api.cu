@@ -104,6 +104,9 @@ static int check_pool_errors(crl_engine_impl* e) {
   CRL_CUDA(cudaMemcpyAsync(&err, e->P.err, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
   CRL_CUDA(cudaStreamSynchronize(e->stream));
   if (err) {
+    // report once and clear: kernels only OR into the flag, and one overflowing game must not make every later call
+    // on this engine fail (the offending lanes keep whatever partial state they have; callers reload them)
+    CRL_CUDA(cudaMemsetAsync(e->P.err, 0, sizeof(int), e->stream));
     set_error("pool overflow on the device (flags %d: 1 = nodes per game, 2 = edges per game, 4 = plies per game); "
               "create the engine with larger max_nodes / avg_moves", err);
     return CRL_ENOMEM;

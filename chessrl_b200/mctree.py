@@ -93,15 +93,18 @@ class SelfPlayTree(Tree):
         eng.games_set(game._start[None, :], [[B.uci_to_move(m) for m in game._moves]])
         eng.mcts_begin_move()
         eng.mcts_simulate(max_iters, inflight=k)
-        self._refresh_views(eng)
-        if not self.root.children:
-            moves = (Game.NULL_MOVE, Game.NULL_MOVE)
-            return moves if ai_move else moves[0]
-        pick = int(np.argmax(self.compute_policy(self.root, noise=noise)))
-        picks = np.full(eng.max_games, -1, dtype=np.int32)
-        picks[0] = pick
-        out = eng.commit(picks, apply=False)
-        moves = (B.move_to_uci(out[0, 0]), B.move_to_uci(out[0, 1]))
+        # the pick and the commit come BEFORE anything else touches the engine's game lane: building Node views
+        # replays positions through Game.move on the same one-lane engine, which overwrites lane 0
+        st = eng.root_stats(want=("visits",))
+        n_kids = int(st["n_children"][0])
+        moves = (Game.NULL_MOVE, Game.NULL_MOVE)
+        if n_kids:
+            policy = _compute_policy(st["visits"][0, :n_kids], int(st["root_visits"][0]), len(game._moves), noise)
+            picks = np.full(eng.max_games, -1, dtype=np.int32)
+            picks[0] = int(np.argmax(policy))
+            out = eng.commit(picks, apply=False)
+            moves = (B.move_to_uci(out[0, 0]), B.move_to_uci(out[0, 1]))
+        self._attach_views(eng.node_dump(0))
         return moves if ai_move else moves[0]
 
     def compute_policy(self, node, noise=True):
@@ -110,27 +113,55 @@ class SelfPlayTree(Tree):
         return _compute_policy([c.visits for c in node.children], node.visits, n_plies, noise)
 
     # ---- views --------------------------------------------------------------------------------------------
-    def _refresh_views(self, eng):
-        dump = eng.node_dump(0)
+    def _attach_views(self, dump):
+        """Node views from one flat dump of the device tree.  Statistics are filled in at once; a view's `state`
+        (a Game, i.e. a replay on the device) and `unexpanded_actions` are built on first access, so a search costs
+        no per-node replays unless a caller walks the tree."""
         views = []
-        for i, n in enumerate(dump):
+        for n in dump:
             if n.parent < 0:
                 v = self.root
                 v.children = []
+                legal = v.state.get_legal_moves()
+                v.unexpanded_actions = legal[:len(legal) - n.n_children]
             else:
                 parent = views[n.parent]
-                state = parent.state.get_copy()
-                state.move(B.move_to_uci(n.move))
-                if n.reply != B.MOVE_NONE:
-                    state.move(B.move_to_uci(n.reply))
-                v = Node.__new__(Node)
-                v.state, v.children, v.parent, v.vloss = state, [], parent, 0
-                legal = state.get_legal_moves()
-                v.unexpanded_actions = legal[:len(legal) - n.n_children]
+                v = _NodeView(parent, n.move, n.reply, n.n_children)
                 parent.children.append(v)
             v.visits = int(n.visits)
             v.value = float(n.value)
             v.prior = np.float32(n.prior) if n.parent >= 0 and n.prior != 1.0 else 1
             views.append(v)
-        legal = self.root.state.get_legal_moves()
-        self.root.unexpanded_actions = legal[:len(legal) - dump[0].n_children] if dump else legal
+
+
+class _NodeView(Node):
+    """A non-root Node whose Game is replayed only when somebody asks for it."""
+
+    def __init__(self, parent, move, reply, n_children):
+        self.children = []
+        self.parent = parent
+        self.value = 0
+        self.visits = 0
+        self.prior = 1
+        self.vloss = 0
+        self._line = (int(move), int(reply), int(n_children))
+        self._state = None
+        self._unexpanded = None
+
+    @property
+    def state(self):
+        if self._state is None:
+            move, reply, _ = self._line
+            st = self.parent.state.get_copy()
+            st.move(B.move_to_uci(move))
+            if reply != B.MOVE_NONE:
+                st.move(B.move_to_uci(reply))
+            self._state = st
+        return self._state
+
+    @property
+    def unexpanded_actions(self):
+        if self._unexpanded is None:
+            legal = self.state.get_legal_moves()
+            self._unexpanded = legal[:len(legal) - self._line[2]]
+        return self._unexpanded

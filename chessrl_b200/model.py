@@ -15,9 +15,13 @@ Weight pack order (conv kernels HWIO, dense kernels [in][out], BN = gamma, beta,
 
 from __future__ import annotations
 
+import itertools
 import os
 
 import numpy as np
+
+_SERIAL = itertools.count(1)     # process-wide: every weight assignment gets a new serial (never reused, unlike id())
+_HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
 
 N_BLOCKS = 10
 N_FILTERS = 256
@@ -81,14 +85,41 @@ class ChessModel(object):
         if weights:
             self.load_weights(weights)
 
+    @property
+    def weights(self):
+        return self._weights
+
+    @weights.setter
+    def weights(self, pack):
+        """Assigning a pack (constructor, load_weights, the training step, a broadcast) bumps `serial`, the token the
+        engines compare to decide whether their device copy is current (runtime.ensure_weights)."""
+        self._weights = pack
+        self.serial = next(_SERIAL)
+
+    @property
+    def version(self):          # older name of the token
+        return self.serial
+
+    @version.setter
+    def version(self, _):
+        self.serial = next(_SERIAL)
+
     def n_params(self):
         return int(sum(w.size for w in self.weights))
 
     def load_weights(self, weights_path):
         if not os.path.exists(weights_path):
             raise OSError("weights file not found: %s" % weights_path)      # supervised.py:57-59 catches OSError
-        with np.load(weights_path) as z:
-            w = [z["w%03d" % i].astype(np.float32) for i in range(N_TENSORS)]
+        with open(weights_path, "rb") as f:
+            magic = f.read(8)
+        if magic == _HDF5_MAGIC:
+            # a real Keras checkpoint of the reference (model.py:77-81): needs h5py, which this image does not have;
+            # scripts/export_keras_weights.py converts it on the reference side
+            from .keras_h5 import load_keras_h5
+            w = load_keras_h5(weights_path)
+        else:
+            with np.load(weights_path) as z:
+                w = [z["w%03d" % i].astype(np.float32) for i in range(N_TENSORS)]
         for a, sh in zip(w, pack_shapes()):
             if tuple(a.shape) != tuple(sh):
                 raise ValueError("weight shape mismatch %s vs %s" % (a.shape, sh))

@@ -69,15 +69,19 @@ class DataGameSequence(object):
         return int(len(self.dataset) / self.batch_size)
 
     def __getitem__(self, idx):
+        """(planes float64 [N,8,8,127], (policy one-hot float32 [N,1968], value [N])), N = plies of the batch's games.
+        All plies are encoded in one crl_encode launch (training.encode_games) instead of one get_game_state call
+        per sample; the flip draw is the reference's (one np.random.rand() per game)."""
+        import torch
+        from . import training
         games = self.dataset[idx * self.batch_size:(idx + 1) * self.batch_size]
-        xs, pol, val = [], [], []
+        flips = training.draw_flips(len(games), self.random_flips)
+        planes, pol, _ = training.encode_games(games, flips)
+        xs = planes[..., :127].to(torch.float64).cpu().numpy()
+        pol = pol.cpu().numpy()
+        onehot = np.zeros((len(pol), 1968), dtype=np.float32)
+        onehot[np.arange(len(pol)), pol] = 1.0
+        vals = []
         for g in games:
-            samples = self.dataset.augment_game(g)
-            flip = np.random.rand() < self.random_flips
-            for s in samples:
-                xs.append(get_game_state(s['game'], flipped=flip))
-                onehot = np.zeros(1968, dtype=np.float32)
-                onehot[self.uci_ids[s['next_move']]] = 1.0
-                pol.append(onehot)
-                val.append(s['result'])
-        return np.asarray(xs), (np.asarray(pol), np.asarray(val))
+            vals.extend([g.get_result()] * len(g))               # the result as stored: None for an unfinished game
+        return xs, (onehot, np.asarray(vals))

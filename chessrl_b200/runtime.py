@@ -25,7 +25,7 @@ def scalar_engine(min_nodes=1024, min_inflight=1):
 def ensure_weights(engine, model):
     """Uploads `model`'s weight pack to the scalar engine unless it is already there."""
     global _loaded_token
-    token = (id(model), getattr(model, "version", 0))
+    token = model.serial        # process-wide, bumped by every weight assignment (model.ChessModel.weights)
     if engine is _scalar:
         if _loaded_token != token:
             engine.load_weights(model.weights)

@@ -54,7 +54,6 @@ def broadcast_weights(model, src=0):
         out.append(flat[o:o + w.size].reshape(w.shape).astype(np.float32))
         o += w.size
     model.weights = out
-    model.version = getattr(model, "version", 0) + 1
 
 
 def pack_games(move_words, results, colors):

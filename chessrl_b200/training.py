@@ -11,6 +11,8 @@ planes are rotated by 180 degrees with probability 0.1 while the policy target i
 
 from __future__ import annotations
 
+import random
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -59,34 +61,140 @@ def forward_logits(p, planes_nhwc, training):
     return logits, value
 
 
-def encode_games(games, flips, device):
-    """Planes [N,8,8,128] bf16 for every ply of every game, plus targets."""
-    eng = runtime.scalar_engine()
-    labels = {u: i for i, u in enumerate(get_uci_labels())}
+_LABEL_IDS = None
+
+
+def _label_ids():
+    global _LABEL_IDS
+    if _LABEL_IDS is None:
+        _LABEL_IDS = {u: i for i, u in enumerate(get_uci_labels())}
+    return _LABEL_IDS
+
+
+def draw_flips(n_games, random_flips):
+    """One `np.random.rand() < random_flips` per game in batch order, the draw DataGameSequence.__getitem__ makes
+    (netencoder.py:168) -- same calls, so numpy's global stream advances as the reference's does."""
+    return [bool(np.random.rand() < random_flips) for _ in range(n_games)]
+
+
+def game_samples(games, flips):
+    """Host arrays for every ply of every game, the samples DatasetGame.augment_game lists (dataset.py:21-43):
+    boards [N,9], history bitboards [N,8,8] (most recent first, zero where the stack is exhausted), history lengths
+    [N], policy target index [N], value target [N] (white-point-of-view result, 0 for an unfinished game), flip [N]."""
+    labels = _label_ids()
     boards, hists, hlens, pol, val, flip_rows = [], [], [], [], [], []
     for g, flip in zip(games, flips):
+        n = len(g._moves)
+        if n == 0:
+            continue
+        recs = np.stack(g._records[:n + 1]).astype(np.uint64)
+        ply = np.arange(n)
+        idx = ply[:, None] - 1 - np.arange(8)[None, :]            # position i+1 plies back, i = 0..7
+        h = recs[np.clip(idx, 0, None)][:, :, :8].copy()
+        h[idx < 0] = 0
         result = g.get_result()
-        recs = g._records
-        for ply, mv in enumerate(g._moves):
-            boards.append(recs[ply])
-            prev = recs[:ply][::-1][:8]
-            h = np.zeros((8, 8), dtype=np.uint64)
-            for i, r in enumerate(prev):
-                h[i] = r[:8]
-            hists.append(h)
-            hlens.append(len(prev))
-            pol.append(labels[mv])
-            val.append(0.0 if result is None else float(result))
-            flip_rows.append(flip)
-    n = len(boards)
-    bt = eng.boards_to_device(np.stack(boards))
-    ht = torch.from_numpy(np.ascontiguousarray(np.stack(hists).transpose(1, 2, 0)).view(np.int64)).to(eng.device)
-    lt = torch.tensor(hlens, dtype=torch.uint8, device=eng.device)
+        boards.append(recs[:n])
+        hists.append(h)
+        hlens.append(np.minimum(ply, 8))
+        pol.append(np.array([labels[m] for m in g._moves], dtype=np.int64))
+        val.append(np.full(n, 0.0 if result is None else float(result), dtype=np.float32))
+        flip_rows.append(np.full(n, bool(flip)))
+    if not boards:
+        z = np.zeros
+        return z((0, 9), np.uint64), z((0, 8, 8), np.uint64), z(0, np.uint8), z(0, np.int64), z(0, np.float32), z(0, bool)
+    return (np.concatenate(boards), np.concatenate(hists), np.concatenate(hlens).astype(np.uint8), np.concatenate(pol),
+            np.concatenate(val), np.concatenate(flip_rows))
+
+
+def encode_games(games, flips, device=None):
+    """Planes [N,8,8,128] bf16 (crl_encode) for every ply of every game plus the targets (policy index, value), the
+    batch DataGameSequence.__getitem__ builds (netencoder.py:159-181): a game's planes are rotated by 180 degrees when
+    its flip is set, its policy target is not (reference quirk, kept)."""
+    eng = runtime.scalar_engine()
+    boards, hists, hlens, pol, val, flip_rows = game_samples(games, flips)
+    n = boards.shape[0]
+    if n == 0:
+        return (torch.zeros((0, 8, 8, 128), dtype=torch.bfloat16, device=eng.device),
+                torch.zeros(0, dtype=torch.int64, device=eng.device), torch.zeros(0, device=eng.device))
+    bt = eng.boards_to_device(boards)
+    ht = torch.from_numpy(np.ascontiguousarray(hists.transpose(1, 2, 0)).view(np.int64)).to(eng.device)
+    lt = torch.from_numpy(hlens).to(eng.device)
     planes = eng.encode(bt, ht, lt)
-    fr = torch.tensor(flip_rows, dtype=torch.bool, device=eng.device)
-    if fr.any():
+    if flip_rows.any():
+        fr = torch.from_numpy(flip_rows).to(eng.device)
         planes = torch.where(fr.view(n, 1, 1, 1), planes.flip(1, 2), planes)      # np.rot90(k=2) over (H, W)
-    return planes, torch.tensor(pol, device=eng.device), torch.tensor(val, dtype=torch.float32, device=eng.device)
+    return planes, torch.from_numpy(pol).to(eng.device), torch.from_numpy(val).to(eng.device)
+
+
+class KerasAdam:
+    """tf.keras.optimizers.Adam(lr=0.002) (model.py:69) step for step: beta_1 0.9, beta_2 0.999, epsilon 1e-7 applied
+    as the paper's "epsilon hat":  lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  w -= lr_t * m / (sqrt(v) + eps).
+    (torch.optim.Adam puts eps next to sqrt(v_hat) instead, which differs where gradients are tiny.)"""
+
+    def __init__(self, params, lr=0.002, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.params = list(params)
+        self.lr, self.b1, self.b2, self.eps = lr, beta_1, beta_2, epsilon
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.t = 0
+
+    @torch.no_grad()
+    def step(self, grads):
+        self.t += 1
+        lr_t = self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t)
+        torch._foreach_mul_(self.m, self.b1)
+        torch._foreach_add_(self.m, grads, alpha=1.0 - self.b1)
+        torch._foreach_mul_(self.v, self.b2)
+        torch._foreach_addcmul_(self.v, grads, grads, value=1.0 - self.b2)
+        denom = torch._foreach_sqrt(self.v)
+        torch._foreach_add_(denom, self.eps)
+        torch._foreach_addcdiv_(self.params, self.m, denom, value=-lr_t)
+
+
+def loss_terms(params, planes, pol, val, training=True):
+    """The compiled Keras loss (model.py:68-72 + kernel_regularizer='l2' on every conv / dense layer):
+    mean categorical cross-entropy(one-hot of the move played) + mean squared error(value, result) + 0.01 * sum w^2.
+    Returns (total, policy_loss, value_loss, regulariser, logits)."""
+    logits, value = forward_logits(params, planes, training=training)
+    loss_p = F.cross_entropy(logits, pol)
+    loss_v = F.mse_loss(value, val)
+    reg = sum((params[i] ** 2).sum() for i in _kernel_indices()) * L2
+    return loss_p + loss_v + reg, loss_p, loss_v, reg, logits
+
+
+def trainable_indices():
+    """Everything but the BatchNorm moving statistics (those are updated by the forward pass, momentum 0.99)."""
+    from .model import pack_shapes
+    return [i for i, s in enumerate(pack_shapes()) if not (len(s) == 1 and _is_bn_running(i))]
+
+
+def train_step(params, opt, planes, pol, val):
+    """One fit_generator batch: forward in training mode (BatchNorm batch statistics, moving statistics updated in
+    place), backward, Adam.  Returns the history record of the batch."""
+    total, loss_p, loss_v, reg, logits = loss_terms(params, planes, pol, val, training=True)
+    grads = torch.autograd.grad(total, opt.params)
+    opt.step(list(grads))
+    acc = (logits.argmax(1) == pol).float().mean().item()
+    return {"loss": total.item(), "policy_loss": loss_p.item(), "value_loss": loss_v.item(), "reg": reg.item(),
+            "policy_acc": acc}
+
+
+def validate(params, val_games, batch_size, dev):
+    """The validation generator of Agent.train (agent.py:73-75): `batch_size` games per batch, no flips; Keras
+    averages the per-batch means over the batches."""
+    bs = max(1, min(batch_size, len(val_games)))
+    sums, n = {"val_loss": 0.0, "val_policy_loss": 0.0, "val_value_loss": 0.0, "val_policy_acc": 0.0}, 0
+    with torch.no_grad():
+        for b in range(len(val_games) // bs):
+            batch = val_games[b * bs:(b + 1) * bs]
+            planes, pol, val = encode_games(batch, [False] * len(batch), dev)
+            total, loss_p, loss_v, _, logits = loss_terms(params, planes, pol, val, training=False)
+            sums["val_loss"] += total.item()
+            sums["val_policy_loss"] += loss_p.item()
+            sums["val_value_loss"] += loss_v.item()
+            sums["val_policy_acc"] += (logits.argmax(1) == pol).float().mean().item()
+            n += 1
+    return {k: v / max(n, 1) for k, v in sums.items()}
 
 
 def train(model, dataset, epochs=1, logdir=None, batch_size=1, validation_split=0, verbose=True):
@@ -97,44 +205,40 @@ def train(model, dataset, epochs=1, logdir=None, batch_size=1, validation_split=
     if validation_split > 0:
         split = len(games) - int(validation_split * len(games))
         games, val_games = games[:split], games[split:]
-    params = [torch.tensor(w, device=dev, requires_grad=False) for w in model.weights]
-    from .model import pack_shapes
-    shapes = pack_shapes()
-    trainable = []
-    for i, s in enumerate(shapes):
-        is_bn_stat = len(s) == 1 and _is_bn_running(i)
-        if not is_bn_stat:
+    # fp32 like the reference's CPU TensorFlow: no TF32 convolutions / matmuls inside the training step
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        params = [torch.tensor(w, device=dev, requires_grad=False) for w in model.weights]
+        trainable = []
+        for i in trainable_indices():
             params[i].requires_grad_(True)
             trainable.append(params[i])
-    opt = torch.optim.Adam(trainable, lr=0.002, eps=1e-7)
-    kidx = _kernel_indices()
-    bs = max(1, min(batch_size, len(games))) if games else 1
-    history = []
-    for ep in range(epochs):
-        for b in range(len(games) // bs):
-            batch = games[b * bs:(b + 1) * bs]
-            flips = [np.random.rand() < 0.1 for _ in batch]
-            planes, pol, val = encode_games(batch, flips, dev)
-            logits, value = forward_logits(params, planes, training=True)
-            loss_p = F.cross_entropy(logits, pol)
-            loss_v = F.mse_loss(value, val)
-            reg = sum((params[i] ** 2).sum() for i in kidx) * L2
-            loss = loss_p + loss_v + reg
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            opt.step()
-            acc = (logits.argmax(1) == pol).float().mean().item()
-            history.append({"epoch": ep, "batch": b, "loss": loss.item(), "policy_loss": loss_p.item(),
-                            "value_loss": loss_v.item(), "policy_acc": acc})
-            if verbose:
-                print("epoch %d batch %d loss %.4f (policy %.4f value %.4f) acc %.3f" %
-                      (ep, b, loss.item(), loss_p.item(), loss_v.item(), acc))
-        if val_games:
-            with torch.no_grad():
-                planes, pol, val = encode_games(val_games, [False] * len(val_games), dev)
-                logits, value = forward_logits(params, planes, training=False)
-                history.append({"epoch": ep, "val_policy_loss": F.cross_entropy(logits, pol).item(),
-                                "val_value_loss": F.mse_loss(value, val).item()})
+        opt = KerasAdam(trainable, lr=0.002, epsilon=1e-7)
+        bs = max(1, min(batch_size, len(games))) if games else 1
+        history = []
+        for ep in range(epochs):
+            order = list(range(len(games) // bs))
+            random.shuffle(order)                    # fit_generator shuffles a Sequence's batch order every epoch
+            for b in order:
+                batch = games[b * bs:(b + 1) * bs]
+                flips = draw_flips(len(batch), 0.1)                      # agent.py:82-84: random_flips=.1
+                planes, pol, val = encode_games(batch, flips, dev)
+                rec = train_step(params, opt, planes, pol, val)
+                rec.update({"epoch": ep, "batch": b})
+                history.append(rec)
+                if verbose:
+                    print("epoch %d batch %d loss %.4f (policy %.4f value %.4f) acc %.3f" %
+                          (ep, b, rec["loss"], rec["policy_loss"], rec["value_loss"], rec["policy_acc"]))
+            if val_games:
+                rec = validate(params, val_games, batch_size, dev)
+                rec["epoch"] = ep
+                history.append(rec)
+                if verbose:
+                    print("epoch %d val_loss %.4f (policy %.4f value %.4f) val_acc %.3f" %
+                          (ep, rec["val_loss"], rec["val_policy_loss"], rec["val_value_loss"], rec["val_policy_acc"]))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
     model.weights = [p.detach().cpu().numpy().astype(np.float32) for p in params]
     if logdir is not None:
         import json

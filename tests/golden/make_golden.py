@@ -366,6 +366,59 @@ def gen_rules(ref):
                              "executed on the python-chess restatement", "cases": recs}, f)
 
 
+def gen_training_batches(ref):
+    """the training input pipeline.  The reference's own DatasetGame.augment_game (dataset.py:21-43) and
+    netencoder.DataGameSequence.__getitem__ (netencoder.py:159-181) run on three stored games; the flip draw
+    (`np.random.rand() < random_flips`, one per game) is steered by random_flips = 0 / 1 and by seeding numpy."""
+    fools = ["f2f3", "e7e5", "g2g4", "d8h4"]                                         # 0-1
+    scholars = ["e2e4", "e7e5", "d1h5", "b8c6", "f1c4", "g8f6", "h5f7"]             # 1-0
+    games_moves = [fools, scholars, random_game_moves(ref, 41, 30)]                  # the third one is unfinished
+    colors = [True, False, True]
+    games = []
+    for moves, col in zip(games_moves, colors):
+        g = ref.game.Game(player_color=col, date="01/01/2020 00:00:00")
+        for m in moves:
+            assert g.move(m)
+        games.append(g)
+    ds = ref.dataset.DatasetGame(games)
+    aug = []
+    for g in games:
+        samples = ds.augment_game(g)
+        aug.append([{"plies": len(s["game"].board.move_stack), "next_move": s["next_move"], "result": s["result"],
+                     "player_color": s["game"].player_color, "fen": s["game"].board.fen()} for s in samples])
+    base = ref.netencoder.DataGameSequence(ds, batch_size=3, random_flips=0)
+    assert len(base) == 1
+    x0, (p0, v0) = base[0]
+    cases, packed = [], []
+    for name, rf, seed in (("no_flips", 0, None), ("all_flipped", 1.0, None), ("seeded_half_a", 0.5, 1),
+                           ("seeded_half_b", 0.5, 6), ("training_rate_0.1", 0.1, 7)):
+        seq = ref.netencoder.DataGameSequence(ds, batch_size=3, random_flips=rf)
+        if seed is not None:
+            np.random.seed(seed)
+        x, (pol, val) = seq[0]
+        after = float(np.random.rand()) if seed is not None else None     # where the global stream stands afterwards
+        assert x.shape == (sum(len(m) for m in games_moves), 8, 8, 127) and pol.shape == (x.shape[0], 1968)
+        assert (pol == p0).all()                                          # the policy target is never flipped
+        flips, o = [], 0
+        for m in games_moves:
+            same = bool((x[o:o + len(m)] == x0[o:o + len(m)]).all())
+            rot = bool((x[o:o + len(m)] == x0[o:o + len(m), ::-1, ::-1]).all())
+            assert same != rot
+            flips.append(rot)
+            o += len(m)
+        cases.append({"name": name, "random_flips": rf, "seed": seed, "flips": flips, "next_rand": after,
+                      "policy_index": [int(i) for i in pol.argmax(1)], "values": [None if v is None else int(v) for v in val]})
+        packed.append(np.packbits(x.astype(np.uint8).reshape(-1)))
+    np.savez_compressed(os.path.join(OUT, "training_batches.npz"), packed=np.stack(packed))
+    with open(os.path.join(OUT, "training_batches.json"), "w") as f:
+        json.dump({"source": "dataset.DatasetGame.augment_game (dataset.py:21-43) + netencoder.DataGameSequence.__getitem__ "
+                             "(netencoder.py:159-181), reference code executed; training_batches.npz['packed'][i] = "
+                             "np.packbits(x.reshape(-1)) of case i, x float64 [N,8,8,127]",
+                   "games": [{"moves": m, "player_color": c, "result": g.get_result()}
+                             for m, c, g in zip(games_moves, colors, games)],
+                   "augment": aug, "cases": cases}, f)
+
+
 def main():
     ref = ref_on_shims.load_reference()
     if ref is None:
@@ -377,6 +430,7 @@ def main():
     gen_mcts(ref)
     gen_mcts_wave(ref)
     gen_selfplay(ref)
+    gen_training_batches(ref)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)))
 

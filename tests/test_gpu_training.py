@@ -1,0 +1,101 @@
+"""SURVEY 8(f)-1 / 8(f)-2 on the GPU: the training input pipeline (DatasetGame.augment_game, DataGameSequence,
+training.encode_games on the CUDA encode kernel) bit-exact against batches produced by the reference's own code
+(tests/golden/training_batches.*), and the training step on the device against the fp64 restatement of the Keras
+definitions (oracle/train_ref.py)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from chessrl_b200 import model, netencoder, training
+from chessrl_b200.agent import Agent
+from chessrl_b200.dataset import DatasetGame
+from test_training_golden import load_training_golden
+from test_training_step import check_against_ref
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def golden():
+    meta, xs = load_training_golden()
+    ds = DatasetGame()
+    ds.loads(json.dumps([{"moves": g["moves"], "result": g["result"], "player_color": g["player_color"],
+                          "date": "01/01/2020 00:00:00"} for g in meta["games"]]))
+    return meta, xs, ds
+
+
+def test_augment_game_matches_reference(golden):
+    meta, _, ds = golden
+    for gi, g in enumerate(ds.games):
+        assert g.get_result() == meta["games"][gi]["result"]
+        samples = ds.augment_game(g)
+        assert len(samples) == len(meta["augment"][gi])
+        for s, want in zip(samples, meta["augment"][gi]):
+            assert len(s["game"].board.move_stack) == want["plies"]
+            assert s["next_move"] == want["next_move"] and s["result"] == want["result"]
+            assert s["game"].player_color == want["player_color"]
+            assert s["game"].board.fen() == want["fen"]
+
+
+def test_data_game_sequence_matches_reference_batches(golden):
+    """Planes, policy one-hot, values -- flipped and unflipped -- and the state of numpy's global RNG afterwards."""
+    meta, xs, ds = golden
+    for case, want in zip(meta["cases"], xs):
+        seq = netencoder.DataGameSequence(ds, batch_size=3, random_flips=case["random_flips"])
+        assert len(seq) == 1
+        if case["seed"] is not None:
+            np.random.seed(case["seed"])
+        x, (pol, val) = seq[0]
+        assert x.dtype == np.float64 and x.shape == want.shape and pol.shape == (want.shape[0], 1968)
+        assert (x == want).all(), case["name"]
+        assert list(pol.argmax(1)) == case["policy_index"] and (pol.sum(1) == 1).all()
+        assert list(val) == case["values"]
+        if case["seed"] is not None:
+            assert float(np.random.rand()) == case["next_rand"]
+
+
+def test_encode_games_flips_planes_but_not_the_policy_target(golden):
+    meta, xs, ds = golden
+    for case, want in zip(meta["cases"], xs):
+        planes, pol, val = training.encode_games(ds.games, case["flips"])
+        assert planes.dtype == torch.bfloat16 and tuple(planes.shape) == (want.shape[0], 8, 8, 128)
+        assert (planes[..., 127] == 0).all()
+        assert (planes[..., :127].float().cpu().numpy() == want).all(), case["name"]
+        assert pol.tolist() == case["policy_index"]
+        assert val.tolist() == [0.0 if v is None else float(v) for v in case["values"]]
+
+
+def test_training_step_on_the_device_matches_fp64_restatement():
+    import train_ref
+    from test_training_step import _batch
+    pack = model.random_pack(seed=21, perturb_bn=True)
+    x, pol, val = _batch(n_positions=24, seed=6)
+    tr = training.trainable_indices()
+    ref = train_ref.loss_and_grads(pack, x, pol, val, tr)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        check_against_ref(pack, x, pol, val, tr, *ref, device="cuda")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_agent_train_runs_batched_with_validation(golden, tmp_path, capsys):
+    """Agent.train (agent.py:64-89) with a validation split: the validation pass streams batch_size games per batch."""
+    _, _, ds = golden
+    many = DatasetGame(list(ds.games) * 2)                      # 6 games: 4 train (2 batches of 2), 2 validation
+    agent = Agent(True)
+    before = [w.copy() for w in agent.model.weights]
+    serial = agent.model.serial
+    agent.train(many, epochs=1, logdir=str(tmp_path), batch_size=2, validation_split=0.34)
+    assert agent.model.serial != serial
+    log = [json.loads(l) for l in open(tmp_path / "train_log.jsonl")]
+    batches = [r for r in log if "batch" in r]
+    vals = [r for r in log if "val_loss" in r]
+    assert len(batches) == 2 and len(vals) == 1
+    assert all(np.isfinite(r["loss"]) and r["policy_loss"] > 5 for r in batches)
+    assert np.isfinite(vals[0]["val_loss"]) and "val_loss" in capsys.readouterr().out
+    moved = sum(float(np.abs(a - b).max()) > 0 for a, b in zip(agent.model.weights, before))
+    assert moved >= 90                                          # every kernel / bias / gamma / beta and the BN statistics

@@ -58,3 +58,58 @@ def test_fen_record_roundtrip_keeps_every_field():
         assert B.fen_from_record(rec, True) == fen                 # ep square printed when a capture is legal
         if parts[3] != "-":
             assert B.fen_from_record(rec, False) == " ".join(parts[:3] + ["-"] + parts[4:])
+
+
+def test_model_serial_is_bumped_by_every_weight_assignment(tmp_path):
+    """runtime.ensure_weights compares ChessModel.serial (process-wide, never reused) instead of id(model)."""
+    from chessrl_b200.model import ChessModel
+    a, b = ChessModel(seed=0), ChessModel(seed=1)
+    assert a.serial != b.serial
+    s = a.serial
+    a.weights = [w.copy() for w in a.weights]
+    assert a.serial > s
+    path = str(tmp_path / "model-0.h5")
+    a.save_weights(path)
+    s = b.serial
+    b.load_weights(path)                                  # direct load_weights also counts as a new set of weights
+    assert b.serial > s and all(np.array_equal(x, y) for x, y in zip(a.weights, b.weights))
+    serials = {ChessModel(seed=0).serial for _ in range(5)}      # objects freed in between still get fresh serials
+    assert len(serials) == 5
+
+
+def test_keras_checkpoint_layer_mapping_and_hdf5_detection(tmp_path):
+    """model.py:77-81 reads Keras .h5 files: layers are matched by kind and creation order whatever numbers Keras
+    appended to their names; a real HDF5 file without h5py gives a clear error, not a pickle crash."""
+    import pytest
+    from chessrl_b200 import keras_h5
+    from chessrl_b200.model import ChessModel, random_pack
+    pack = random_pack(seed=9, perturb_bn=True)
+    for first in (0, 23, 46):                             # first, second, third model built in the writing process
+        layers = keras_h5.keras_layers_from_pack(pack, first_suffix=first)
+        assert len(layers) == 23 + 22 + 3
+        if first == 0:
+            assert "conv2d" in layers and "batch_normalization_21" in layers and "dense" in layers
+        # Keras also lists weightless layers (Input, Activation, Add, Flatten) with empty weight lists
+        layers["activation_%d" % (first + 1)] = {}
+        got = keras_h5.pack_from_keras_layers(dict(reversed(list(layers.items()))))     # file order does not matter
+        assert all(np.array_equal(a, b) for a, b in zip(got, pack))
+    broken = keras_h5.keras_layers_from_pack(pack)
+    del broken["conv2d_7"]
+    with pytest.raises(ValueError):
+        keras_h5.pack_from_keras_layers(broken)
+    swapped = keras_h5.keras_layers_from_pack(pack)
+    swapped["conv2d_21"], swapped["conv2d_22"] = swapped["conv2d_22"], swapped["conv2d_21"]
+    with pytest.raises(ValueError):                       # policy / value head convolutions swapped: shapes give it away
+        keras_h5.pack_from_keras_layers(swapped)
+    fake = tmp_path / "model-1.h5"
+    fake.write_bytes(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    try:
+        import h5py  # noqa: F401
+        has_h5py = True
+    except ImportError:
+        has_h5py = False
+    if not has_h5py:
+        with pytest.raises(RuntimeError, match="export_keras_weights"):
+            ChessModel(weights=str(fake))
+    with pytest.raises(OSError):
+        ChessModel(weights=str(tmp_path / "missing.h5"))   # supervised.py:57-59 catches OSError for a missing file
