@@ -57,6 +57,7 @@ SIGNATURES = {
     "crl_net_load_host": (ctypes.c_int, [vp, ctypes.POINTER(c_f32p), c_i64p, ctypes.c_int]),
     "crl_net_forward": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, vp]),
     "crl_debug_conv": (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int]),
+    "crl_debug_tower": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]),
     "crl_hash_eval": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int, vp, vp]),
     "crl_set_evaluator": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]),
     "crl_games_set_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u64p, c_u16p, c_i32p, ctypes.c_int]),
@@ -84,13 +85,16 @@ class CrlError(RuntimeError):
 
 
 def load():
-    """Loads (building it with nvcc if the sources are newer) the CUDA library.  Raises if that fails."""
+    """Loads the CUDA library.  It is built with nvcc first only when the .so is missing or CRL_REBUILD is set --
+    deliberately NOT on source mtimes: a snapshot copied to a GPU box carries arbitrary mtimes, and several ranks
+    importing at once must not start concurrent builds.  After editing csrc/ run `python -m chessrl_b200.build`
+    (or __graft_entry__.build()).  Raises if the library cannot be loaded."""
     global _lib
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH) or os.environ.get("CRL_REBUILD"):
         from . import build as _build
-        _build.build()
+        _build.build(force=True)
     if not os.path.exists(LIB_PATH):
         raise ImportError("libchessrl_b200.so is missing and could not be built; the CUDA extension is required "
                           "(there is no CPU fallback)")

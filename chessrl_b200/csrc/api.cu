@@ -553,6 +553,16 @@ int crl_debug_conv(crl_engine* e, int layer, const void* in_dev, int cin, int n,
   return net_debug_conv(e, layer, (const __nv_bfloat16*)in_dev, cin, n, (const __nv_bfloat16*)residual_dev,
                         (__nv_bfloat16*)out_dev, relu);
 }
+int crl_debug_tower(crl_engine* e, const void* planes_bf16_dev, int n, int layer, void* act_out_dev, float* logits_out_dev,
+                    void* pf_out_dev, float* vf_out_dev, float* policy_dev, float* value_dev) {
+  CHECK_ENGINE(e);
+  if (!planes_bf16_dev || !policy_dev || !value_dev) {
+    set_error("crl_debug_tower: null planes / policy / value");
+    return CRL_EINVAL;
+  }
+  return net_debug_tower(e, (const __nv_bfloat16*)planes_bf16_dev, n, layer, (__nv_bfloat16*)act_out_dev, logits_out_dev,
+                         (__nv_bfloat16*)pf_out_dev, vf_out_dev, policy_dev, value_dev);
+}
 int crl_hash_eval(crl_engine* e, const uint64_t* boards_dev, int n, uint64_t seed, int policy_bits, float* policy_dev,
                   float* value_dev) {
   CHECK_ENGINE(e);

@@ -143,7 +143,9 @@ void net_destroy(crl_engine_impl* e);
 int net_load(crl_engine_impl* e, const float* const* w, const int64_t* sizes, int n);
 // n_dev may be null (then n_host rows); otherwise the row count is read on the device and n_host is the bound
 int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, const int* n_dev, float* policy,
-                float* value);
+                float* value, __nv_bfloat16* dbg_out = nullptr, int dbg_layer = -1);
+int net_debug_tower(crl_engine_impl* e, const __nv_bfloat16* planes, int n, int layer, __nv_bfloat16* act_out,
+                    float* logits_out, __nv_bfloat16* pf_out, float* vf_out, float* policy, float* value);
 int net_debug_conv(crl_engine_impl* e, int layer, const __nv_bfloat16* in, int cin, int n, const __nv_bfloat16* residual,
                    __nv_bfloat16* out, int relu);
 

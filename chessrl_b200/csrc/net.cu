@@ -771,6 +771,8 @@ struct TrunkParams {
   const float* head_s;
   __nv_bfloat16* pf_out;
   float* vf_out;
+  __nv_bfloat16* dbg_out;   // test tap (crl_debug_tower): layer dbg_layer's output [boards][64][256], else null
+  int dbg_layer;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
@@ -1001,6 +1003,12 @@ k_trunk(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __res
 // ten pixels), group g = 2*y + board.  Rows of a tile are therefore ordered (y, board, x) instead of (board, y, x);
 // the epilogue un-permutes when it computes its global row.  Per (tile, layer) a CTA now reads 4 x 25.6 KB of
 // activations instead of 36 x 16 KB; the weight stream (36 x 16 KB) is unchanged and gets its own, deeper ring.
+//
+// Activation scratch is indexed by CTA-PAIR SLOT, not by board: a pair carries its group of 8 boards through all 21
+// layers before it takes the next group, so the two ping-pong buffers only need 8 boards per pair
+// (74 pairs x 8 boards x 32 KB x 2 = 39 MB).  That footprint stays resident in the 126 MB L2 and every line is
+// overwritten by the next layer before it is evicted, so the activations stop being written back to HBM
+// (board-indexed buffers: 2 x 134 MB per 4,096-position batch, 4.85 x the algorithmic DRAM traffic).
 // ======================================================================================================
 // ring sizes are template parameters: T4_NA padded-image slots, T4_NB weight stages (default 3 / 7)
 static constexpr int T4_IMG_ROWS = 200;                   // 10 x 2 x 10
@@ -1093,8 +1101,10 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
           for (int kc = 0; kc < ld.k_chunks; ++kc) {
             mbar_wait(&a_empty[as], aphase ^ 1);
             if (rank == 0) mbar_arrive_expect_tx(&a_full[as], 2 * T4_IMG_BYTES);
-            // coordinates (channel, x, board, y): the box {64, 10, 2, 10} starts one pixel outside the board
-            tma2_load_4d(smem_a + as * T4_A_SLOT, map_a, &a_full[as], kc * BLOCK_K, -1, tile * 4 + (int)rank * 2, -1);
+            // coordinates (channel, x, board, y): the box {64, 10, 2, 10} starts one pixel outside the board.
+            // The planes are indexed by board, the activation scratch by this pair's slot.
+            const int b0 = (ld.map_in == 0 ? tile * 4 : pair * 8 + X * 4) + (int)rank * 2;
+            tma2_load_4d(smem_a + as * T4_A_SLOT, map_a, &a_full[as], kc * BLOCK_K, -1, b0, -1);
             if (rank != 0) mbar_arrive_remote(&a_full[as], 0);
             if (++as == T4_NA) {
               as = 0;
@@ -1177,10 +1187,12 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
           mbar_wait(&tmem_full[X], (uint32_t)(uses & 1));
           tcgen05_fence_after();
           const int board = tile * 4 + (int)rank * 2 + eb;
-          const long long grow = (long long)board * 64 + ey * 8 + ex;
+          const long long grow = (long long)board * 64 + ey * 8 + ex;                    // row by board (heads, tap)
+          const long long srow = (long long)(pair * 8 + X * 4 + (int)rank * 2 + eb) * 64 + ey * 8 + ex;   // row by slot
           const bool valid = board < n_boards;
-          __nv_bfloat16* orow = ld.write_out ? ld.out + grow * TILE_N : nullptr;
-          const __nv_bfloat16* rrow = ld.residual ? ld.residual + grow * TILE_N : nullptr;
+          __nv_bfloat16* orow = ld.write_out ? ld.out + srow * TILE_N : nullptr;
+          const __nv_bfloat16* rrow = ld.residual ? ld.residual + srow * TILE_N : nullptr;
+          __nv_bfloat16* drow = (p.dbg_out && L == p.dbg_layer) ? p.dbg_out + grow * TILE_N : nullptr;
           float h0 = 0.f, h1 = 0.f, h2 = 0.f;
 #pragma unroll 1
           for (int c0 = 0; c0 < TILE_N; c0 += 32) {
@@ -1220,7 +1232,7 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
                 h2 = fmaf(x, s_hw[512 + c0 + j], h2);
               }
             }
-            if (orow) {
+            if (orow || drow) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 uint32_t pk[4];
@@ -1229,7 +1241,8 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
                   __nv_bfloat162 b2 = __floats2bfloat162_rn(a[8 * j + 2 * h], a[8 * j + 2 * h + 1]);
                   pk[h] = *reinterpret_cast<uint32_t*>(&b2);
                 }
-                *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (orow) *reinterpret_cast<uint4*>(orow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                if (drow) *reinterpret_cast<uint4*>(drow + c0 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               }
             }
           }
@@ -1373,9 +1386,12 @@ struct NetWeights {
   // v4 (tower kernel with the padded-image A operand reused across the nine taps)
   bool use_trunk4 = true;
   int t4_ring = 0;                          // index into the instantiated (image slots, weight stages) pairs
+  __nv_bfloat16* act4[2] = {nullptr, nullptr};  // [n_sms/2 pairs x 8 boards][64][256]: ping-pong scratch by CTA-pair slot
+  int act4_rows = 0;
   CUtensorMap map_act4[2];
   CUtensorMap map_planes4;
   CUtensorMap* d_maps4 = nullptr;
+  LayerDesc* d_layers4 = nullptr;           // [N_CONVS], out / residual pointing into act4
   // v3 (whole tower in one persistent kernel)
   bool use_trunk = true;
   CUtensorMap* d_maps = nullptr;            // [3 + N_CONVS] device copies: (unused: the planes map is a kernel
@@ -1478,11 +1494,26 @@ int net_create(crl_engine_impl* e) {
     if ((rc = make_w_map(nw, &nw->map_pf, nw->pf, 128, nw->cap_rows + 256, 128))) return rc;
     if ((rc = make_w_map(nw, &nw->map_wp, nw->wp_bf16, 128, 2048, 128))) return rc;
   }
-  for (int i = 0; i < 2; ++i) {
-    if ((rc = dev_alloc(e, &nw->act[i], (size_t)nw->cap_rows * 64 * 256))) return rc;
-    CRL_CUDA(cudaMemsetAsync(nw->act[i], 0, (size_t)nw->cap_rows * 64 * 256 * 2, e->stream));
-    if ((rc = make_act_map(nw, &nw->map_act[i], nw->act[i], 256, nw->cap_rows))) return rc;
-    if ((rc = make_act_map4(nw, &nw->map_act4[i], nw->act[i], 256, nw->cap_rows))) return rc;
+  {
+    // which tower runs is fixed at creation (debug knobs), so only its activation buffers are allocated
+    const char* nt = getenv("CRL_NO_TRUNK");
+    const char* t3 = getenv("CRL_TRUNK_V3");
+    nw->use_trunk = nw->use_v2 && !(nt && nt[0] == '1');
+    nw->use_trunk4 = nw->use_trunk && !(t3 && t3[0] == '1');
+  }
+  if (nw->use_trunk4) {
+    nw->act4_rows = (nw->n_sms / 2) * 8;
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = dev_alloc(e, &nw->act4[i], (size_t)nw->act4_rows * 64 * 256))) return rc;
+      CRL_CUDA(cudaMemsetAsync(nw->act4[i], 0, (size_t)nw->act4_rows * 64 * 256 * 2, e->stream));
+      if ((rc = make_act_map4(nw, &nw->map_act4[i], nw->act4[i], 256, nw->act4_rows))) return rc;
+    }
+  } else {
+    for (int i = 0; i < 2; ++i) {
+      if ((rc = dev_alloc(e, &nw->act[i], (size_t)nw->cap_rows * 64 * 256))) return rc;
+      CRL_CUDA(cudaMemsetAsync(nw->act[i], 0, (size_t)nw->cap_rows * 64 * 256 * 2, e->stream));
+      if ((rc = make_act_map(nw, &nw->map_act[i], nw->act[i], 256, nw->cap_rows))) return rc;
+    }
   }
   if ((rc = dev_alloc(e, &nw->w1x1, 3 * 256))) return rc;
   if ((rc = dev_alloc(e, &nw->s1x1, 6))) return rc;
@@ -1507,18 +1538,15 @@ int net_create(crl_engine_impl* e) {
   }
   {
     // tensor-map table + layer table for the whole-tower kernel
-    const char* nt = getenv("CRL_NO_TRUNK");
-    nw->use_trunk = nw->use_v2 && !(nt && nt[0] == '1');
     if ((rc = dev_alloc(e, &nw->d_maps, 3 + N_CONVS))) return rc;
     if ((rc = dev_alloc(e, &nw->d_layers, N_CONVS))) return rc;
+    if ((rc = dev_alloc(e, &nw->d_layers4, N_CONVS))) return rc;
     std::vector<CUtensorMap> hm(3 + N_CONVS);
     memset(hm.data(), 0, hm.size() * sizeof(CUtensorMap));
     hm[1] = nw->map_act[0];
     hm[2] = nw->map_act[1];
     for (int i = 0; i < N_CONVS; ++i) hm[3 + i] = nw->map_w2[i];
     CRL_CUDA(cudaMemcpyAsync(nw->d_maps, hm.data(), hm.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
-    const char* t3 = getenv("CRL_TRUNK_V3");
-    nw->use_trunk4 = nw->use_trunk && !(t3 && t3[0] == '1');
     if ((rc = dev_alloc(e, &nw->d_maps4, 3 + N_CONVS))) return rc;
     std::vector<CUtensorMap> hm4(hm);
     hm4[1] = nw->map_act4[0];
@@ -1526,33 +1554,37 @@ int net_create(crl_engine_impl* e) {
     CRL_CUDA(cudaMemcpyAsync(nw->d_maps4, hm4.data(), hm4.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, e->stream));
     CRL_CUDA(cudaStreamSynchronize(e->stream));   // hm4 is a local
     std::vector<LayerDesc> hl(N_CONVS);
-    for (int L = 0; L < N_CONVS; ++L) {
-      LayerDesc& d = hl[L];
-      memset(&d, 0, sizeof(d));
-      d.map_w = 3 + L;
-      d.k_chunks = nw->cin[L] / BLOCK_K;
-      d.scale = nw->scale[L];
-      d.shift = nw->shift[L];
-      if (L == 0) {                      // stem: planes -> act[0], no BN / activation
-        d.map_in = 0;
-        d.out = nw->act[0];
-        d.write_out = 1;
-      } else if ((L - 1) % 2 == 0) {     // conv_a: act[0] -> act[1], BN + ReLU
-        d.map_in = 1;
-        d.out = nw->act[1];
-        d.relu = 1;
-        d.write_out = 1;
-      } else {                           // conv_b: act[1] -> act[0] in place (+ residual act[0]), BN, ReLU
-        d.map_in = 2;
-        d.out = nw->act[0];
-        d.residual = nw->act[0];
-        d.relu = 1;
-        d.write_out = L != N_CONVS - 1;  // the last layer only feeds the fused heads
-        d.fuse_heads = L == N_CONVS - 1;
+    for (int variant = 0; variant < 2; ++variant) {     // 0: board-indexed buffers (v3), 1: slot-indexed scratch (v4)
+      __nv_bfloat16* const* act = variant ? nw->act4 : nw->act;
+      for (int L = 0; L < N_CONVS; ++L) {
+        LayerDesc& d = hl[L];
+        memset(&d, 0, sizeof(d));
+        d.map_w = 3 + L;
+        d.k_chunks = nw->cin[L] / BLOCK_K;
+        d.scale = nw->scale[L];
+        d.shift = nw->shift[L];
+        if (L == 0) {                      // stem: planes -> act[0], no BN / activation
+          d.map_in = 0;
+          d.out = act[0];
+          d.write_out = 1;
+        } else if ((L - 1) % 2 == 0) {     // conv_a: act[0] -> act[1], BN + ReLU
+          d.map_in = 1;
+          d.out = act[1];
+          d.relu = 1;
+          d.write_out = 1;
+        } else {                           // conv_b: act[1] -> act[0] in place (+ residual act[0]), BN, ReLU
+          d.map_in = 2;
+          d.out = act[0];
+          d.residual = act[0];
+          d.relu = 1;
+          d.write_out = L != N_CONVS - 1;  // the last layer only feeds the fused heads
+          d.fuse_heads = L == N_CONVS - 1;
+        }
       }
+      CRL_CUDA(cudaMemcpyAsync(variant ? nw->d_layers4 : nw->d_layers, hl.data(), hl.size() * sizeof(LayerDesc),
+                               cudaMemcpyHostToDevice, e->stream));
+      CRL_CUDA(cudaStreamSynchronize(e->stream));
     }
-    CRL_CUDA(cudaMemcpyAsync(nw->d_layers, hl.data(), hl.size() * sizeof(LayerDesc), cudaMemcpyHostToDevice, e->stream));
-    CRL_CUDA(cudaStreamSynchronize(e->stream));
   }
   return CRL_OK;
 }
@@ -1767,7 +1799,7 @@ static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, flo
 }
 
 int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, const int* n_dev, float* policy,
-                float* value) {
+                float* value, __nv_bfloat16* dbg_out, int dbg_layer) {
   NetWeights* nw = e->net;
   if (!nw || !nw->loaded) {
     set_error("network weights are not loaded (crl_net_load_host)");
@@ -1799,6 +1831,8 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     tp.head_s = nw->s1x1;
     tp.pf_out = nw->pf;
     tp.vf_out = nw->vf;
+    tp.dbg_out = dbg_out;
+    tp.dbg_layer = dbg_layer;
     int groups = ((n_host + 3) / 4 + 1) / 2;
     int pairs = groups < nw->n_sms / 2 ? groups : nw->n_sms / 2;
     if (pairs < 1) pairs = 1;
@@ -1807,10 +1841,10 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
       if (nw->use_trunk4) {
         const dim3 grid(2 * pairs), block(CONV_THREADS);
         switch (nw->t4_ring) {
-          case 1: k_trunk4<3, 8><<<grid, block, t4_smem_bytes(3, 8), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
-          case 2: k_trunk4<2, 9><<<grid, block, t4_smem_bytes(2, 9), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
-          case 3: k_trunk4<2, 10><<<grid, block, t4_smem_bytes(2, 10), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
-          default: k_trunk4<3, 7><<<grid, block, t4_smem_bytes(3, 7), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers, tp); break;
+          case 1: k_trunk4<3, 8><<<grid, block, t4_smem_bytes(3, 8), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers4, tp); break;
+          case 2: k_trunk4<2, 9><<<grid, block, t4_smem_bytes(2, 9), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers4, tp); break;
+          case 3: k_trunk4<2, 10><<<grid, block, t4_smem_bytes(2, 10), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers4, tp); break;
+          default: k_trunk4<3, 7><<<grid, block, t4_smem_bytes(3, 7), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers4, tp); break;
         }
       } else
         k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
@@ -1872,6 +1906,34 @@ int net_debug_conv(crl_engine_impl* e, int layer, const __nv_bfloat16* in, int c
   if (rc) return rc;
   if (nw->use_v2) return launch_conv_v2(e, m, layer, nullptr, n, residual, out, relu, false);
   return launch_conv(e, m, layer, nullptr, n, residual, out, relu);
+}
+
+
+// test hook (crl_debug_tower): the production forward pass -- k_trunk4 + policy GEMM + softmax/value kernel -- with a
+// tap on convolution `layer`'s output and copies of the head inputs / policy logits
+int net_debug_tower(crl_engine_impl* e, const __nv_bfloat16* planes, int n, int layer, __nv_bfloat16* act_out,
+                    float* logits_out, __nv_bfloat16* pf_out, float* vf_out, float* policy, float* value) {
+  NetWeights* nw = e->net;
+  if (!nw || !nw->loaded) {
+    set_error("network weights are not loaded");
+    return CRL_ESTATE;
+  }
+  if (!nw->use_trunk4) {
+    set_error("crl_debug_tower: the tap exists in the v4 tower kernel only (unset CRL_TRUNK_V3 / CRL_NO_TRUNK / CRL_CONV_V1)");
+    return CRL_ESTATE;
+  }
+  if (n <= 0 || n > nw->cap_rows || (act_out && (layer < 0 || layer >= N_CONVS))) {
+    set_error("crl_debug_tower: bad arguments (n %d of %d, layer %d)", n, nw->cap_rows, layer);
+    return CRL_EINVAL;
+  }
+  int rc = net_forward(e, planes, n, nullptr, policy, value, act_out, layer);
+  if (rc) return rc;
+  if (logits_out)
+    CRL_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)CRL_N_LABELS * 4, nw->logits, 2048 * 4, (size_t)CRL_N_LABELS * 4, n,
+                               cudaMemcpyDeviceToDevice, e->stream));
+  if (pf_out) CRL_CUDA(cudaMemcpyAsync(pf_out, nw->pf, (size_t)n * 128 * 2, cudaMemcpyDeviceToDevice, e->stream));
+  if (vf_out) CRL_CUDA(cudaMemcpyAsync(vf_out, nw->vf, (size_t)n * 64 * 4, cudaMemcpyDeviceToDevice, e->stream));
+  return CRL_OK;
 }
 
 }  // namespace crl

@@ -179,6 +179,21 @@ class Engine:
         check(self.lib.crl_debug_conv(self.h, int(layer), _ptr(x_t), cin, n, _ptr(residual_t), _ptr(out), int(relu)))
         return out
 
+    def debug_tower(self, planes_t, layer=20):
+        """The production forward pass with taps: dict(act = output of convolution `layer` [n,8,8,256] bf16,
+        logits [n,1968], pf [n,128] bf16, vf [n,64], policy [n,1968], value [n])."""
+        n = planes_t.shape[0]
+        dev = self.device
+        out = {"act": torch.zeros((n, 8, 8, 256), dtype=torch.bfloat16, device=dev),
+               "logits": torch.empty((n, _lib.N_LABELS), dtype=torch.float32, device=dev),
+               "pf": torch.empty((n, 128), dtype=torch.bfloat16, device=dev),
+               "vf": torch.empty((n, 64), dtype=torch.float32, device=dev),
+               "policy": torch.empty((n, _lib.N_LABELS), dtype=torch.float32, device=dev),
+               "value": torch.empty((n,), dtype=torch.float32, device=dev)}
+        check(self.lib.crl_debug_tower(self.h, _ptr(planes_t), n, int(layer), _ptr(out["act"]), _ptr(out["logits"]),
+                                       _ptr(out["pf"]), _ptr(out["vf"]), _ptr(out["policy"]), _ptr(out["value"])))
+        return out
+
     def hash_eval(self, boards_t, seed, policy_bits=24):
         n = boards_t.shape[1]
         policy = torch.empty((n, _lib.N_LABELS), dtype=torch.float32, device=self.device)

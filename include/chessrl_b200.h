@@ -135,6 +135,15 @@ int crl_net_forward(crl_engine* e, const void* planes_bf16_dev, int n, float* po
  * optional residual_dev / out_dev [n][8][8][256] bf16 */
 int crl_debug_conv(crl_engine* e, int layer, const void* in_dev, int cin, int n, const void* residual_dev,
                    void* out_dev, int relu);
+/* test hook: the PRODUCTION forward pass (the whole-tower kernel k_trunk4, the policy GEMM, the softmax / value kernel)
+ * on planes_bf16_dev [n][8][8][128], with taps for parity tests against model.py:31-63, 111-122 layer by layer:
+ *   act_out_dev    [n][8][8][256] bf16  output of convolution `layer` (0 = stem, 1..20 = tower; after BatchNorm, skip
+ *                                       connection and ReLU where the graph has them), written by k_trunk4's own epilogue
+ *   logits_out_dev [n][1968] f32        policy logits before the softmax
+ *   pf_out_dev     [n][128] bf16, vf_out_dev [n][64] f32   inputs of the two dense heads (1x1 conv + BN + ReLU, flattened)
+ *   policy_dev [n][1968], value_dev [n] as crl_net_forward.  Any tap may be NULL. */
+int crl_debug_tower(crl_engine* e, const void* planes_bf16_dev, int n, int layer, void* act_out_dev, float* logits_out_dev,
+                    void* pf_out_dev, float* vf_out_dev, float* policy_dev, float* value_dev);
 /* the deterministic test evaluator on raw boards (SoA), same outputs as the oracle's hash_evaluator */
 int crl_hash_eval(crl_engine* e, const uint64_t* boards_dev, int n, uint64_t seed, int policy_bits,
                   float* policy_dev, float* value_dev);

@@ -74,7 +74,8 @@ def test_lockstep_real_network_matches_oracle_visit_counts():
     n_games = int(os.environ.get("CRL_PARITY_GAMES", "64"))
     n_moves = int(os.environ.get("CRL_PARITY_MOVES", "4"))
     sims = int(os.environ.get("CRL_PARITY_SIMS", "48"))
-    pack = model.random_pack(seed=11)
+    import netpacks
+    pack = netpacks.lively_pack()          # live value head: with Keras-default init the value is 0.0 for every position
     eng = Engine(max_games=n_games, max_nodes=sims + 1, avg_moves=96)
     eng.load_weights(pack)
     eng.set_evaluator(EVAL_NET)
@@ -104,6 +105,16 @@ def test_lockstep_real_network_matches_oracle_visit_counts():
                 picks[g] = int(np.argmax(compute_policy(st["visits"][g, :k], st["root_visits"][g], int(plies[g]), False)))
         out = eng.commit(picks, apply=True)
         recorded.append((st, picks.copy(), out.copy()))
+
+    # the value head must be alive, or "value sums match" would be 0.0 == 0.0 and Q would never steer a visit
+    mean_q = []
+    for st, _, _ in recorded:
+        for g in range(n_games):
+            k = int(st["n_children"][g])
+            if k:
+                mean_q.extend(st["values"][g, :k] / np.maximum(st["visits"][g, :k], 1))
+    mean_q = np.asarray(mean_q)
+    assert mean_q.max() - mean_q.min() > 0.1 and np.count_nonzero(mean_q) > 0.9 * mean_q.size, (mean_q.min(), mean_q.max())
 
     # ---- oracle: the same games, one thread each, evaluations batched through crl_net_forward ----
     ev = BatchedNetEvaluator(net, n_games)
