@@ -36,6 +36,18 @@ sys.path.insert(0, ROOT)
 CONV_FLOP_PER_POS = 2 * (3 * 3 * 127 * 256 * 64 + 20 * 3 * 3 * 256 * 256 * 64)   # unpadded, SURVEY.md 8(d)
 NET_FLOP_PER_POS = 1548038656
 KIWI = "r3k2r/p1ppqpb1/bn2pnp1/3PN3/1p2P3/2N2Q1p/PPPBBPPP/R3K2R w KQkq - 0 1"
+RULES_NCU_NOTE = "profiles/r02_ncu_rules_kernels.txt"
+
+
+def measured_tower_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per k_trunk4 launch from the committed ncu capture
+    (profiles/r02_trunk4_dram.json, written by scripts/ncu_trunk_dram.py from the --set full report); None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_trunk4_dram.json")) as f:
+            d = json.load(f)
+        return d
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -93,20 +105,20 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def synthetic_games(engine, n_games, seed):
-    """Start positions for half the lanes, midgame positions (8-60 seeded random legal plies) for the rest.
-    The random plies are generated on the device with the engine's own movegen / make-move kernels."""
+def synthetic_games(engine, n_games, seed, lo=8, hi=60, start_fraction=0.5):
+    """Start positions for `start_fraction` of the lanes, midgame positions (lo..hi seeded random legal plies) for the
+    rest.  The random plies are generated on the device with the engine's own movegen / make-move kernels."""
     import torch
     from chessrl_b200 import boards as B
     gen = torch.Generator(device="cpu").manual_seed(seed)
     target = torch.zeros(n_games, dtype=torch.int64)
-    half = n_games // 2
-    target[half:] = torch.randint(8, 61, (n_games - half,), generator=gen)
+    half = int(n_games * start_fraction)
+    target[half:] = torch.randint(lo, hi + 1, (n_games - half,), generator=gen)
     boards = engine.boards_to_device(np.tile(B.record_from_fen(), (n_games, 1)))
-    rnd = torch.randint(0, 1 << 30, (61, n_games), generator=gen).to(engine.device)
+    rnd = torch.randint(0, 1 << 30, (hi + 1, n_games), generator=gen).to(engine.device)
     target_d = target.to(engine.device)
-    lists = torch.full((n_games, 60), B.MOVE_NONE - 65536, dtype=torch.int16, device=engine.device)
-    for ply in range(60):
+    lists = torch.full((n_games, hi), B.MOVE_NONE - 65536, dtype=torch.int16, device=engine.device)
+    for ply in range(hi):
         moves, counts, _ = engine.movegen(boards)
         alive = (counts > 0) & (target_d > ply)
         idx = (rnd[ply] % counts.clamp(min=1)).to(torch.int64)
@@ -201,31 +213,132 @@ def perft_sharded(engine, rank, world, dist):
     out = {}
     for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690),
                                    ("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
-        frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
-        d = 0
-        while frontier.shape[1] < (65536 if depth <= 5 else (1 << 20)) and d < depth - 1:
-            frontier, _ = engine.expand_frontier(frontier)
-            d += 1
-        mine = frontier[:, rank::world].contiguous()
-        best = None
+        best, best_walk = None, None
         for rep in range(4):
             dist.barrier()
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             a.record()
+            # every rank expands the (small) upper plies itself -- cheaper than scattering boards -- then takes its share
+            frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
+            d = 0
+            while frontier.shape[1] < (65536 if depth <= 5 else (1 << 20)) and d < depth - 1:
+                frontier, _ = engine.expand_frontier(frontier)
+                d += 1
+            mine = frontier[:, rank::world].contiguous()
+            m.record()
             nodes = engine.perft(mine, depth - d, bulk=True)
             b.record()
             torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            t = torch.tensor([a.elapsed_time(b), m.elapsed_time(b)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             total = sharding.sum_counts(nodes)                             # one all_reduce(sum) of an int64
             assert total == want, (name, total, want)
             if rep > 0:
-                best = float(t.item()) if best is None else min(best, float(t.item()))
+                best = float(t[0].item()) if best is None else min(best, float(t[0].item()))
+                best_walk = float(t[1].item()) if best_walk is None else min(best_walk, float(t[1].item()))
         out[name] = {"nodes": want, "ms_max_over_ranks": best, "nodes_per_s": want / best * 1e3,
+                     "timed": "frontier expansion (replicated on every rank, host-driven plies) + this rank's walk",
+                     "ms_walk_only_max_over_ranks": best_walk, "nodes_per_s_walk_only": want / best_walk * 1e3,
                      "frontier_boards": int(frontier.shape[1]), "boards_per_rank": int(mine.shape[1]),
                      "leaf_bulk_counting": True}
     return out
+
+
+def whole_games_steady_state(model_pack, lanes, sims, inflight, n_steps, seed):
+    """The path selfplay.py runs (chessrl_b200.selfplay.LockstepRun: harvest finished games -> refill their lanes ->
+    one lockstep move for all lanes incl. the host-side move pick) in its steady state, timed by WALL CLOCK.
+    Lanes start at staggered phases (0..300 random plies) so games end -- and lanes are harvested and refilled -- at
+    their natural rate inside the timed window; the supply of games is unbounded, so there is no drain tail here
+    (a finite run's tail is measured by `bench.py --whole-games N`, profiles/)."""
+    import torch
+    from chessrl_b200._lib import EVAL_NET
+    from chessrl_b200.engine import Engine
+    from chessrl_b200.selfplay import LockstepRun, edge_slots_per_node
+    eng = Engine(max_games=lanes, max_nodes=sims + 1, max_inflight=inflight, avg_moves=edge_slots_per_node(lanes, sims + 1))
+    eng.load_weights(model_pack)
+    eng.set_evaluator(EVAL_NET)
+    start, move_lists = synthetic_games(eng, lanes, seed, lo=0, hi=300, start_fraction=0.0)
+    run = LockstepRun(None, None, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, engine=eng)
+    np.random.seed(seed)
+    run.start(start_records=start, move_lists=eng.pack_move_lists(move_lists))
+    run.advance()                                                   # warm-up step (graph capture, first refills)
+    torch.cuda.synchronize()
+    c0, f0, r0, m0 = eng.counters(), run.finished_games, run.refills, run.sp.moves_played
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        run.advance()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    c1 = eng.counters()
+    sims_done = c1["simulations"] - c0["simulations"]
+    out = {"workload": "%d lanes x %d sims/move, %d lockstep moves, unbounded game supply, lanes at staggered phases" %
+                       (lanes, sims, n_steps),
+           "timing": "wall clock around LockstepRun.advance() x %d (harvest + refill + search + host move pick + commit)" % n_steps,
+           "seconds": dt, "simulations_per_s": sims_done / dt, "agent_moves": run.sp.moves_played - m0,
+           "games_finished": run.finished_games - f0, "lanes_refilled": run.refills - r0,
+           "games_per_s_at_this_phase_mix": (run.finished_games - f0) / dt,
+           "lane_occupancy": sims_done / max(1, n_steps * lanes * sims),
+           "evaluations_per_simulation": (c1["evaluations"] - c0["evaluations"]) / max(1, sims_done)}
+    eng.close()
+    return out
+
+
+def whole_games_complete_run(model_pack, n_games, lanes, sims, inflight, seed):
+    """A complete finite self-play run through chessrl_b200.selfplay.play_games_lockstep, drain tail included."""
+    from chessrl_b200 import model
+    from chessrl_b200.selfplay import play_games_lockstep
+    m = model.ChessModel()
+    m.weights = model_pack
+    np.random.seed(seed)
+    stats = {}
+    data = play_games_lockstep(m, n_games, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, stats=stats)
+    res = [g.get_result() for g in data.games]
+    stats.update({"games": len(data), "mean_plies": float(np.mean([len(g) for g in data.games])),
+                  "white_wins": res.count(1), "black_wins": res.count(-1), "draws": res.count(0), "unfinished": res.count(None),
+                  "simulations_per_s_wall_clock": stats["simulations"] / stats["seconds"],
+                  "games_per_s": len(data) / stats["seconds"]})
+    return stats
+
+
+def large_config(pack, world, rank, dist, barrier, K):
+    """BASELINE configs[4] (65,536 games x 800 sims/move sharded by game over the ranks) when there are >= 2 ranks;
+    on one GPU the >= 65k-concurrent-games claim: 65,536 games x 200 sims/move.  One timed step after a short warm-up."""
+    import torch
+    from chessrl_b200._lib import EVAL_NET
+    from chessrl_b200.engine import Engine
+    G2 = 65536 // world
+    S2 = 800 if world > 1 else 200
+    eng = Engine(max_games=G2, max_nodes=S2 + 1, avg_moves=64, max_inflight=K)
+    eng.load_weights(pack)
+    eng.set_evaluator(EVAL_NET)
+    start, move_lists = synthetic_games(eng, G2, seed=4321 + rank)
+    eng.games_set(start, eng.pack_move_lists(move_lists))
+    eng.mcts_begin_move()
+    eng.mcts_simulate(4, K)                                         # warm-up: graph capture, tensor maps
+    barrier()
+    c0 = eng.counters()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    eng.mcts_begin_move()
+    eng.mcts_simulate(S2, K)
+    b.record()
+    barrier()
+    ms = a.elapsed_time(b)
+    c1 = eng.counters()
+    sims = float(c1["simulations"] - c0["simulations"])
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([sims], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t)
+        sims = float(t.item())
+    eng.close()
+    return {"workload": ("BASELINE configs[4]: 65,536 games x 800 sims/move sharded by game over %d GPUs (%d games per GPU)" % (world, G2))
+            if world > 1 else "65,536 concurrent games on ONE GPU x 200 sims/move (north_star: >= 65k concurrent games)",
+            "games_total": G2 * world, "games_per_gpu": G2, "sims_per_move": S2, "steps": 1, "ms_per_step_max_over_ranks": ms,
+            "simulations": sims, "simulations_per_s": sims / (ms * 1e-3), "tower": "k_trunk4"}
 
 
 def _time_launch(fn, flush, reps=5):
@@ -268,8 +381,8 @@ def kernel_rooflines(engine, peaks, flush, net_loaded):
     ms = _time_launch(lambda: check(engine.lib.crl_movegen(engine.h, _ptr(boards), n, _ptr(moves), _ptr(counts), None)), flush)
     avg_l = float(counts.float().mean().item())
     byt = n * (72 + 2 * avg_l + 4)
-    out["movegen"] = {"bound": "INT32 ALU pipe (64-bit bitboard logic on the half-rate integer pipe; ncu before the set-wise rule core: pipe_alu "
-                               "71.7 % of peak, profiles/r01_ncu_rules_kernels_after_opt.txt), then hbm", "boards": n, "avg_legal_moves": avg_l, "us": ms * 1e3,
+    out["movegen"] = {"bound": "INT32 ALU pipe (64-bit bitboard logic on the half-rate integer pipe), then hbm; ncu pipe / issue-slot "
+                               "figures of the current build: " + RULES_NCU_NOTE, "boards": n, "avg_legal_moves": avg_l, "us": ms * 1e3,
                       "boards_per_s": n / ms * 1e3, "achieved": byt / ms / 1e6, "peak": hbm, "unit": "GB/s",
                       "frac": byt / ms / 1e6 / hbm, "algorithmic_bytes_per_board": 72 + 2 * avg_l + 4}
     first = moves[:, 0].contiguous()
@@ -477,6 +590,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-perft", action="store_true")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline section")
+    ap.add_argument("--no-whole-games", action="store_true", help="skip the steady-state whole-game leg")
+    ap.add_argument("--wg-steps", type=int, default=10, help="lockstep moves timed in the steady-state whole-game leg")
+    ap.add_argument("--no-large", action="store_true", help="skip the configs[4] / 65,536-games leg")
+    ap.add_argument("--whole-games", type=int, default=0, help="also play this many COMPLETE games (drain included)")
+    ap.add_argument("--wg-lanes", type=int, default=None)
+    ap.add_argument("--wg-sims", type=int, default=None)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -585,6 +704,7 @@ def main():
     # ---- roofline of the dominant kernel (conv), measured live with CUDA events around every conv launch ----
     roof = None
     prof = None
+    TRAFFIC = measured_tower_traffic()
     if rank == 0:
         eng.profile(True)
         c0 = eng.counters()
@@ -610,11 +730,12 @@ def main():
                                    "kernel sustains more than cuBLAS did in the driver's 4 s matmul loop on this pod",
                     "peak_burst": peaks["bf16_tflops"], "frac_of_burst": achieved / peaks["bf16_tflops"],
                     "flop_per_launch": flop_per_launch, "us_per_launch": t_launch * 1e6,
-                    # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full, 4,096 positions, mean of 2 captured
-                    # launches (profiles/r01_ncu_trunk_v4.txt): 219.6 MB read + 234.1 MB written.  Algorithmic minimum: 67 MB
-                    # planes in + 24.8 MB weights + 1.6 MB head features out; the rest is write-back of the two 134 MB
-                    # activation buffers that L2 (126 MB) cannot hold entirely -- 1.4 % of the HBM peak, not a limiter
-                    "traffic": (456.7e6 if v3 else 453.7e6) if (G == 4096 and K == 1) else None, "traffic_unit": "bytes/launch",
+                    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of
+                    # this kernel at 4,096 positions (read from profiles/, not pasted).  Algorithmic minimum: 67.1 MB planes in
+                    # + 24.8 MB weights + 1.6 MB head features out = 93.5 MB
+                    "traffic": (TRAFFIC or {}).get("dram_bytes_per_launch") if (G == 4096 and K == 1 and not v3) else None,
+                    "traffic_unit": "bytes/launch", "traffic_source": (TRAFFIC or {}).get("source"),
+                    "traffic_algorithmic": 93.5e6,
                     "share_of_step_ms": {k: round(v["ms"], 3) for k, v in prof.items()}}
 
     # ---- perft (secondary metric) and CPU baseline, rank 0 only ----
@@ -634,6 +755,17 @@ def main():
             perft["cpu_baseline"] = cpu_perft_baseline()
     if rank == 0 and not args.no_kernels:
         kernels = kernel_rooflines(eng, peaks, flush, True)
+    whole = None
+    complete = None
+    large = None
+    eng.close()                                      # the legs below size their own engines
+    if rank == 0 and not args.no_whole_games:
+        whole = whole_games_steady_state(pack, args.wg_lanes or G, args.wg_sims or S, K, args.wg_steps, seed=7)
+        whole["fraction_of_device_resident_value"] = whole["simulations_per_s"] / (value / world) if (args.wg_lanes or G) == G and (args.wg_sims or S) == S else None
+    if rank == 0 and args.whole_games > 0:
+        complete = whole_games_complete_run(pack, args.whole_games, args.wg_lanes or G, args.wg_sims or S, K, seed=7)
+    if not args.no_large:
+        large = large_config(pack, world, rank, dist, barrier, K)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         best, one, par = cpu_baseline_best(12.0)
         cpu = {"value": best["value"], "unit": "simulations/s", "cores": best["cores"], "kind": "port",
@@ -661,9 +793,9 @@ def main():
             "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
             "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
             "roofline": roof, "cpu_baseline": cpu, "perft": perft, "perft_sharded": perft_multi, "kernels": kernels,
+            "whole_games": whole, "whole_games_complete_run": complete, "large_config": large,
         }
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

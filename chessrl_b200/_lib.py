@@ -64,6 +64,10 @@ SIGNATURES = {
     "crl_games_get_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u64p, c_i32p, c_i8p]),
     "crl_games_set_active_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u8p]),
     "crl_game_moves_host": (ctypes.c_int, [vp, ctypes.c_int, c_u16p, ctypes.c_int, c_i32p]),
+    "crl_games_restart_host": (ctypes.c_int, [vp, c_i32p, ctypes.c_int, c_u64p]),
+    "crl_games_moves_host": (ctypes.c_int, [vp, c_i32p, ctypes.c_int, c_u16p, ctypes.c_int, c_i32p]),
+    "crl_games_play_host": (ctypes.c_int, [vp, c_u16p, c_u8p]),
+    "crl_games_legal_host": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_u16p, c_i32p]),
     "crl_games_policy_move_host": (ctypes.c_int, [vp, c_u8p, c_u16p]),
     "crl_mcts_begin_move": (ctypes.c_int, [vp]),
     "crl_mcts_simulate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int]),

@@ -673,6 +673,98 @@ int crl_game_moves_host(crl_engine* e, int game, uint16_t* moves_host, int cap, 
   return CRL_OK;
 }
 
+int crl_games_restart_host(crl_engine* e, const int32_t* lanes_host, int n, const uint64_t* start_host) {
+  CHECK_ENGINE(e);
+  if (n < 0 || (n > 0 && (!lanes_host || !start_host))) {
+    set_error("crl_games_restart_host: bad arguments");
+    return CRL_EINVAL;
+  }
+  if (n == 0) return CRL_OK;
+  for (int i = 0; i < n; ++i)
+    if (lanes_host[i] < 0 || lanes_host[i] >= e->G) {
+      set_error("crl_games_restart_host: lane %d out of range (capacity %d)", lanes_host[i], e->G);
+      return CRL_EINVAL;
+    }
+  const size_t b_lanes = ((size_t)n * 4 + 7) / 8 * 8;
+  int rc = ensure_stage(e, 72 + b_lanes);
+  if (rc) return rc;
+  char* h = (char*)e->h_stage;
+  char* d = (char*)e->d_stage;
+  memcpy(h, start_host, 72);
+  memcpy(h + 72, lanes_host, (size_t)n * 4);
+  CRL_CUDA(cudaMemcpyAsync(d, h, 72 + b_lanes, cudaMemcpyHostToDevice, e->stream));
+  rc = launch_games_replay(e, 0, n, (const u64*)d, nullptr, nullptr, 1, nullptr, nullptr, nullptr, (const int*)(d + 72));
+  if (rc) return rc;
+  e->tree_ready = false;
+  return check_pool_errors(e);
+}
+
+int crl_games_moves_host(crl_engine* e, const int32_t* lanes_host, int n, uint16_t* moves_host, int cap, int32_t* n_moves_host) {
+  CHECK_ENGINE(e);
+  if (n < 0 || cap <= 0 || (n > 0 && (!lanes_host || !moves_host || !n_moves_host))) {
+    set_error("crl_games_moves_host: bad arguments");
+    return CRL_EINVAL;
+  }
+  if (n == 0) return CRL_OK;
+  for (int i = 0; i < n; ++i)
+    if (lanes_host[i] < 0 || lanes_host[i] >= e->G) {
+      set_error("crl_games_moves_host: lane %d out of range (capacity %d)", lanes_host[i], e->G);
+      return CRL_EINVAL;
+    }
+  const size_t b_lanes = ((size_t)n * 4 + 7) / 8 * 8, b_cnt = b_lanes, b_mv = (size_t)n * cap * 2;
+  int rc = ensure_stage(e, b_lanes + b_cnt + b_mv);
+  if (rc) return rc;
+  char* h = (char*)e->h_stage;
+  char* d = (char*)e->d_stage;
+  memcpy(h, lanes_host, (size_t)n * 4);
+  CRL_CUDA(cudaMemcpyAsync(d, h, b_lanes, cudaMemcpyHostToDevice, e->stream));
+  rc = launch_gather_moves(e, (const int*)d, n, cap, (u16*)(d + b_lanes + b_cnt), (int*)(d + b_lanes));
+  if (rc) return rc;
+  CRL_CUDA(cudaMemcpyAsync(h + b_lanes, d + b_lanes, b_cnt + b_mv, cudaMemcpyDeviceToHost, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));
+  memcpy(n_moves_host, h + b_lanes, (size_t)n * 4);
+  memcpy(moves_host, h + b_lanes + b_cnt, b_mv);
+  return CRL_OK;
+}
+
+int crl_games_play_host(crl_engine* e, const uint16_t* moves_host, uint8_t* accepted_host) {
+  CHECK_ENGINE(e);
+  if (!moves_host) {
+    set_error("crl_games_play_host: null moves");
+    return CRL_EINVAL;
+  }
+  const size_t G = e->G, b_mv = (G * 2 + 7) / 8 * 8;
+  int rc = ensure_stage(e, b_mv + G);
+  if (rc) return rc;
+  char* h = (char*)e->h_stage;
+  char* d = (char*)e->d_stage;
+  memcpy(h, moves_host, G * 2);
+  CRL_CUDA(cudaMemcpyAsync(d, h, b_mv, cudaMemcpyHostToDevice, e->stream));
+  rc = launch_game_moves(e, (const u16*)d, (u8*)(d + b_mv));
+  if (rc) return rc;
+  e->tree_ready = false;
+  if (accepted_host) CRL_CUDA(cudaMemcpyAsync(accepted_host, d + b_mv, G, cudaMemcpyDeviceToHost, e->stream));
+  return check_pool_errors(e);
+}
+
+int crl_games_legal_host(crl_engine* e, int first, int n, uint16_t* legal_host, int32_t* n_legal_host) {
+  CHECK_ENGINE(e);
+  if (first < 0 || n <= 0 || first + n > e->G || !legal_host || !n_legal_host) {
+    set_error("crl_games_legal_host: bad arguments (first %d, n %d, capacity %d)", first, n, e->G);
+    return CRL_EINVAL;
+  }
+  const size_t b_legal = (size_t)n * MAX_MOVES * 2, b_cnt = (size_t)n * 4;
+  int rc = ensure_stage(e, b_legal + b_cnt);
+  if (rc) return rc;
+  char* d = (char*)e->d_stage;
+  rc = launch_game_info(e, first, n, (u16*)d, (int*)(d + b_legal));
+  if (rc) return rc;
+  CRL_CUDA(cudaMemcpyAsync(legal_host, d, b_legal, cudaMemcpyDeviceToHost, e->stream));
+  CRL_CUDA(cudaMemcpyAsync(n_legal_host, d + b_legal, b_cnt, cudaMemcpyDeviceToHost, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));
+  return CRL_OK;
+}
+
 int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t* picks_host) {
   CHECK_ENGINE(e);
   const size_t G = e->G;

@@ -127,7 +127,8 @@ int launch_hash_eval_boards(crl_engine_impl* e, const u64* boards, int n, u64 se
 // tree / game
 int launch_games_replay(crl_engine_impl* e, int first, int n, const u64* start_aos, const u16* moves,
                         const int* n_moves, int stride, u8* accepted, u64* records = nullptr,
-                        int* n_records = nullptr);
+                        int* n_records = nullptr, const int* lanes = nullptr);
+int launch_gather_moves(crl_engine_impl* e, const int* lanes, int n, int cap, u16* out, int* n_out);
 int launch_game_info(crl_engine_impl* e, int first, int n, u16* legal, int* n_legal);
 int launch_game_moves(crl_engine_impl* e, const u16* moves_per_game /*[G]*/, u8* accepted /*[G] or null*/);
 int launch_eval_batch(crl_engine_impl* e, int which_mode);   // encodes eval_list rows and runs the evaluator

@@ -285,7 +285,8 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, const float
 }
 
 // ---- game records -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first, int n,
+// lanes != null: game i goes to lane lanes[i] (scattered refill) and all games share start_aos[0..8]
+__global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first, int n, const int* __restrict__ lanes,
                                                              const u64* __restrict__ start_aos,
                                                              const u16* __restrict__ moves,
                                                              const int* __restrict__ n_moves, int stride,
@@ -293,8 +294,8 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first,
                                                              int* __restrict__ n_records) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const int g = first + i;
-  Board b = load_rec(start_aos + 9LL * i);
+  const int g = lanes ? lanes[i] : first + i;
+  Board b = load_rec(lanes ? start_aos : start_aos + 9LL * i);
   // a fresh record starts with an empty move stack (Board(fen) / Game())
   b.meta = meta_pack(meta_turn(b.meta), meta_castle(b.meta), meta_ep(b.meta), meta_halfmove(b.meta),
                      meta_fullmove(b.meta), 0, 0);
@@ -338,6 +339,18 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_game_moves(Pools P, const u16* _
   if (accepted) accepted[g] = (u8)ok;
 }
 
+// move lists of the listed lanes (finished games on their way to gameplays.json): one block per lane
+__global__ void __launch_bounds__(TREE_BLOCK) k_gather_moves(Pools P, const int* __restrict__ lanes, int n, int cap,
+                                                             u16* __restrict__ out, int* __restrict__ n_out) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const int g = lanes[i];
+  const int m = P.g_nmoves[g];
+  if (threadIdx.x == 0) n_out[i] = m;
+  const u16* src = P.g_moves + (long long)g * MAX_GAME_PLIES;
+  for (int k = threadIdx.x; k < min(m, cap); k += blockDim.x) out[(long long)i * cap + k] = src[k];
+}
+
 // search_move's return value (mctree.py:178-198) for the chosen root child of every game
 __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __restrict__ pick,
                                                        u16* __restrict__ out_moves, int apply) {
@@ -366,16 +379,22 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __res
 
 // ---- launchers ----------------------------------------------------------------------------------------
 int launch_games_replay(crl_engine_impl* e, int first, int n, const u64* start_aos, const u16* moves,
-                        const int* n_moves, int stride, u8* accepted, u64* records, int* n_records) {
+                        const int* n_moves, int stride, u8* accepted, u64* records, int* n_records, const int* lanes) {
   LaunchScope ls(e, KC_GAME);
-  k_games_replay<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, start_aos, moves, n_moves, stride,
-                                                                      accepted, records, n_records);
+  k_games_replay<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, lanes, start_aos, moves, n_moves,
+                                                                      stride, accepted, records, n_records);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }
 int launch_game_info(crl_engine_impl* e, int first, int n, u16* legal, int* n_legal) {
   LaunchScope ls(e, KC_GAME);
   k_game_info<<<div_up(n, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, first, n, legal, n_legal);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
+int launch_gather_moves(crl_engine_impl* e, const int* lanes, int n, int cap, u16* out, int* n_out) {
+  LaunchScope ls(e, KC_GAME);
+  k_gather_moves<<<n, TREE_BLOCK, 0, e->stream>>>(e->P, lanes, n, cap, out, n_out);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

@@ -255,6 +255,42 @@ class Engine:
         check(self.lib.crl_game_moves_host(self.h, int(game), _np(buf, ctypes.c_uint16), len(buf), ctypes.byref(n)))
         return buf[:n.value].copy()
 
+    def games_restart(self, lanes, start_record=None):
+        """A new game (from `start_record`, default the start position) in every listed lane: one device round trip."""
+        ln = np.ascontiguousarray(np.asarray(lanes, dtype=np.int32))
+        if ln.size == 0:
+            return
+        rec = np.ascontiguousarray(B.record_from_fen() if start_record is None else np.asarray(start_record, dtype=np.uint64))
+        check(self.lib.crl_games_restart_host(self.h, _np(ln, ctypes.c_int32), int(ln.size), _np(rec, ctypes.c_uint64)))
+
+    def games_moves(self, lanes, cap=2048):
+        """Move lists of the listed lanes in one round trip -> list of uint16 arrays."""
+        ln = np.ascontiguousarray(np.asarray(lanes, dtype=np.int32))
+        if ln.size == 0:
+            return []
+        buf = np.zeros((ln.size, cap), dtype=np.uint16)
+        cnt = np.zeros(ln.size, dtype=np.int32)
+        check(self.lib.crl_games_moves_host(self.h, _np(ln, ctypes.c_int32), int(ln.size), _np(buf, ctypes.c_uint16), int(cap),
+                                            _np(cnt, ctypes.c_int32)))
+        return [buf[i, :min(int(cnt[i]), cap)].copy() for i in range(ln.size)]
+
+    def games_play(self, moves):
+        """Game.move of one optional move word per lane (MOVE_NONE = none) -> bool [max_games] accepted."""
+        mv = np.ascontiguousarray(np.asarray(moves, dtype=np.uint16))
+        assert mv.shape == (self.max_games,)
+        acc = np.zeros(self.max_games, dtype=np.uint8)
+        check(self.lib.crl_games_play_host(self.h, _np(mv, ctypes.c_uint16), _np(acc, ctypes.c_uint8)))
+        torch.cuda.current_stream(self.device).synchronize()
+        return acc.astype(bool)
+
+    def games_legal(self, first=0, n=None):
+        """Legal moves (python-chess order) of lanes first..first+n-1 -> (uint16 [n, 256], int32 [n])."""
+        n = self.max_games - first if n is None else n
+        legal = np.zeros((n, B.MAX_MOVES), dtype=np.uint16)
+        cnt = np.zeros(n, dtype=np.int32)
+        check(self.lib.crl_games_legal_host(self.h, int(first), int(n), _np(legal, ctypes.c_uint16), _np(cnt, ctypes.c_int32)))
+        return legal, cnt
+
     def policy_move(self, mask=None):
         picks = np.zeros(self.max_games, dtype=np.uint16)
         m = None

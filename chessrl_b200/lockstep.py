@@ -97,6 +97,10 @@ class LockstepSelfPlay:
     policy-argmax move (selfplay.py:68-70).  noise=True draws Dirichlet noise from numpy's legacy global RNG in
     game-index order, once per game per move (the reference draws once per move of its single game).
     inflight: simulations in flight per game (the reference's `threads`; needs Engine(max_inflight >= inflight)).
+
+    Host round trips per move: root statistics, the commit, and one status read (plies + results) that harvest /
+    running / the next step's move pick all reuse; harvest and refill are one batched call each whatever the number
+    of lanes involved.
     """
 
     def __init__(self, engine, n_games=None, sims=900, noise=True, refill=False, inflight=1):
@@ -111,6 +115,12 @@ class LockstepSelfPlay:
         self.moves_played = 0
         self._harvested = np.zeros(self.n, dtype=bool)
         self._retired = np.zeros(self.n, dtype=bool)
+        self._plies = np.zeros(self.n, dtype=np.int32)
+        self._results = np.full(self.n, B.RESULT_NONE, dtype=np.int8)
+
+    def _read_status(self):
+        _, plies, results = self.e.games_get(0, self.n)
+        self._plies, self._results = plies, results
 
     def start(self, colors=None, start_records=None, move_lists=None):
         if colors is not None:
@@ -119,7 +129,13 @@ class LockstepSelfPlay:
             start_records = np.tile(B.record_from_fen(), (self.n, 1))
         self.e.games_set(start_records, move_lists)
         if not self.colors.all():
-            self.e.policy_move(mask=(~self.colors).astype(np.uint8))
+            self.e.policy_move(mask=self._lane_mask(~self.colors))
+        self._read_status()
+
+    def _lane_mask(self, flags):
+        mask = np.zeros(self.e.max_games, dtype=np.uint8)
+        mask[:self.n] = np.asarray(flags, dtype=np.uint8)
+        return mask
 
     def step(self):
         """One agent move (+ reply) for every running game.  Returns the (our move, reply) words [n, 2]."""
@@ -127,63 +143,62 @@ class LockstepSelfPlay:
         e.mcts_begin_move()
         e.mcts_simulate(self.sims, self.inflight)
         st = e.root_stats(want=("visits",))
-        _, plies, results = e.games_get(0, self.n)
         picks = np.full(e.max_games, -1, dtype=np.int32)
-        picks[:self.n] = pick_moves(st["visits"][:self.n], st["n_children"][:self.n], st["root_visits"][:self.n], plies,
-                                    (results == B.RESULT_NONE) & ~self._retired, self.noise)
+        picks[:self.n] = pick_moves(st["visits"][:self.n], st["n_children"][:self.n], st["root_visits"][:self.n],
+                                    self._plies, (self._results == B.RESULT_NONE) & ~self._retired, self.noise)
         out = e.commit(picks, apply=True)
         self.moves_played += int((picks >= 0).sum())
+        self._read_status()
         return out[:self.n]
 
     def running(self):
-        _, _, results = self.e.games_get(0, self.n)
-        return (results == B.RESULT_NONE) & ~self._retired
+        return (self._results == B.RESULT_NONE) & ~self._retired
 
     def harvest(self, max_plies=None):
         """Finished games since the last call: list of (lane, moves u16[], result, player_color); also kept in
         self.finished as (moves, result, player_color).  max_plies: games that reached that many plies are
         harvested unfinished (result None), like a capped play_game run.  With refill=True the lanes are restarted."""
-        _, plies, results = self.e.games_get(0, self.n)
-        over = results != B.RESULT_NONE
+        over = self._results != B.RESULT_NONE
         if max_plies is not None:
-            over = over | (plies >= max_plies)
+            over = over | (self._plies >= max_plies)
         done = np.nonzero(over & ~self._harvested & ~self._retired)[0]
         out = []
-        for g in done:
-            res = None if results[g] == B.RESULT_NONE else int(results[g])
-            out.append((int(g), self.e.game_moves(int(g)), res, bool(self.colors[g])))
-            self._harvested[g] = True
+        if len(done):
+            lists = self.e.games_moves(done)                   # one round trip for all of them
+            for g, moves in zip(done, lists):
+                res = None if self._results[g] == B.RESULT_NONE else int(self._results[g])
+                out.append((int(g), moves, res, bool(self.colors[g])))
+                self._harvested[g] = True
         self.finished.extend((m, r, c) for _, m, r, c in out)
         if self.refill and len(done):
             self.restart(done, [self.colors[g] for g in done])
         return out
 
     def restart(self, lanes, colors):
-        """Per-GPU slot refill: a new game from the start position in every listed lane; where the
-        agent plays black the opponent opens with its policy-argmax move (selfplay.py:68-70)."""
-        lanes = [int(g) for g in lanes]
-        if not lanes:
+        """Per-GPU slot refill: a new game from the start position in every listed lane (one batched
+        call); where the agent plays black the opponent opens with its policy-argmax move (selfplay.py:68-70) -- one
+        evaluation batch for all of them."""
+        lanes = np.asarray([int(g) for g in lanes], dtype=np.int32)
+        if lanes.size == 0:
             return
-        start = B.record_from_fen()
-        mask = np.zeros(self.e.max_games, dtype=np.uint8)
-        # contiguous runs of lanes go down in one call each
-        run0 = 0
-        order = sorted(range(len(lanes)), key=lambda i: lanes[i])
-        srt = [lanes[i] for i in order]
-        for i in range(1, len(srt) + 1):
-            if i == len(srt) or srt[i] != srt[i - 1] + 1:
-                self.e.games_set(np.tile(start, (i - run0, 1)), None, first=srt[run0])
-                run0 = i
+        self.e.games_restart(lanes)
+        flags = np.zeros(self.n, dtype=bool)
         for i, g in enumerate(lanes):
             self.colors[g] = bool(colors[i])
             self._harvested[g] = False
             self._retired[g] = False
-            mask[g] = 0 if self.colors[g] else 1
-        if mask.any():
-            self.e.policy_move(mask=mask)
+            flags[g] = not self.colors[g]
+        if flags.any():
+            self.e.policy_move(mask=self._lane_mask(flags))
+        self._plies[lanes] = flags[lanes].astype(np.int32)     # 0 plies, or 1 after the opponent's opening move
+        self._results[lanes] = B.RESULT_NONE
 
     def retire(self, lanes):
         """Lanes that stay empty from now on (no game left to start): step() skips them."""
-        for g in lanes:
-            self._retired[int(g)] = True
-            self.e.games_set_active([0], first=int(g))
+        lanes = [int(g) for g in lanes]
+        if not lanes:
+            return
+        self._retired[lanes] = True
+        active = np.zeros(self.e.max_games, dtype=np.uint8)
+        active[:self.n] = ~self._retired
+        self.e.games_set_active(active, first=0)               # the whole mask in one call

@@ -67,69 +67,135 @@ def edge_slots_per_node(lanes, nodes, device=None, bytes_per_edge=24, share=0.5)
     return max(48, min(218, fit))
 
 
+class LockstepRun:
+    """The many-games form of selfplay.py's game loop (selfplay.py:142-163) on one GPU: `lanes` games advance in
+    lockstep, a lane whose game ends is refilled with the next game at once (per-GPU slot refill) and
+    parked when none is left.  n_games=None means an unbounded supply (steady-state measurements: bench.py).
+
+    advance() = harvest finished games -> refill / park their lanes -> one lockstep move for every running game.
+    """
+
+    def __init__(self, model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
+                 threads=1, evaluator=None, engine=None):
+        import time
+        from ._lib import EVAL_HASH, EVAL_NET
+        from .engine import Engine
+        from .lockstep import LockstepSelfPlay
+        self.n_games = n_games
+        if lanes is None:
+            if n_games is None:
+                raise ValueError("an unbounded run needs an explicit lane count")
+            lanes = n_games
+        self.lanes = lanes = max(1, lanes if n_games is None else min(lanes, n_games))
+        self.sims = sims
+        threads = max(1, min(int(threads), 64))
+        self._own_engine = engine is None
+        self.eng = engine if engine is not None else Engine(
+            max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads,
+            avg_moves=edge_slots_per_node(lanes, sims + 1, device))
+        if evaluator is None:
+            if model is not None:
+                self.eng.load_weights(model.weights)
+            self.eng.set_evaluator(EVAL_NET)
+        else:
+            self.eng.set_evaluator(EVAL_HASH, int(evaluator[1]), int(evaluator[2]))
+        self._rng = random.Random(seed)
+        self._colors = []                                  # colour of game i, drawn like selfplay.py:62
+        self.sp = LockstepSelfPlay(self.eng, n_games=lanes, sims=sims, noise=noise, inflight=threads)
+        # the engine's move lists hold 2,048 plies per game: a game that gets there is stored unfinished instead of
+        # failing the whole run (the fifty-move claim ends games long before that in practice)
+        self.cap = 2040 if max_moves is None else min(2040, 2 * max_moves)
+        self.records = []                                  # (moves, colour) by game index; None while running
+        self.lane_game = list(range(lanes))
+        self.next_game = lanes
+        self.steps = 0
+        self.refills = 0
+        self.finished_games = 0
+        self._time = time
+        self.t0 = time.perf_counter()
+        self.c0 = self.eng.counters()
+        self._started = False
+
+    def _color(self, game):
+        while len(self._colors) <= game:
+            self._colors.append(self._rng.random() >= 0.5)
+        return self._colors[game]
+
+    def _record(self, game, moves, color):
+        while len(self.records) <= game:
+            self.records.append(None)
+        self.records[game] = (moves, color)
+
+    def start(self, start_records=None, move_lists=None):
+        """First fill of the lanes: games 0..lanes-1 (optionally from given prefixes: staggered phases for benchmarks)."""
+        self.sp.start(colors=[self._color(g) for g in range(self.lanes)], start_records=start_records, move_lists=move_lists)
+        self._started = True
+
+    def advance(self):
+        """Returns False once no game is running (a bounded run is then complete)."""
+        if not self._started:
+            self.start()
+        again, parked = [], []
+        for lane, moves, result, color in self.sp.harvest(max_plies=self.cap):
+            self._record(self.lane_game[lane], moves, color)
+            self.finished_games += 1
+            if self.n_games is None or self.next_game < self.n_games:
+                self.lane_game[lane] = self.next_game
+                again.append(lane)
+                self.next_game += 1
+            else:
+                parked.append(lane)
+        self.sp.restart(again, [self._color(self.lane_game[g]) for g in again])   # one batched refill + one opening eval
+        self.refills += len(again)
+        self.sp.retire(parked)
+        if not self.sp.running().any():
+            return False
+        self.sp.step()
+        self.steps += 1
+        return True
+
+    def stats(self):
+        c1 = self.eng.counters()
+        sims = c1["simulations"] - self.c0["simulations"]
+        return {"steps": self.steps, "moves": self.sp.moves_played, "seconds": self._time.perf_counter() - self.t0,
+                "simulations": sims, "evaluations": c1["evaluations"] - self.c0["evaluations"], "lanes": self.lanes,
+                "games_finished": self.finished_games, "refills": self.refills,
+                "lane_occupancy": sims / max(1, self.steps * self.lanes * self.sims)}
+
+    def close(self):
+        if self._own_engine:
+            self.eng.close()
+
+    def dataset(self):
+        out = DatasetGame()
+        for rec in self.records:
+            if rec is None:
+                continue
+            moves, color = rec
+            gm = Game(player_color=color)
+            gm._sync(extra=[B.move_to_uci(m) for m in moves])
+            out.append(gm)
+        return out
+
+
 def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
                         threads=1, evaluator=None, stats=None):
     """`n_games` games in lockstep, `lanes` at a time; returns a DatasetGame in game-start order.
 
-    A lane whose game ends is refilled with the next game at once (per-GPU slot refill), so the
-    evaluation batches stay full until fewer than `lanes` games remain.  The per-move host work is the numpy move
-    policy only.  max_moves caps the agent moves of a game (it is then stored unfinished, result None).
-    evaluator: None = the network with `model`'s weights; ("hash", seed, bits) = the deterministic test evaluator.
-    stats: optional dict that receives steps / moves / simulations / seconds of the run."""
-    import time
-    from ._lib import EVAL_HASH, EVAL_NET
-    from .engine import Engine
-    from .lockstep import LockstepSelfPlay
-    lanes = n_games if lanes is None else max(1, min(lanes, n_games))
-    threads = max(1, min(int(threads), 64))
-    eng = Engine(max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads,
-                 avg_moves=edge_slots_per_node(lanes, sims + 1, device))
-    if evaluator is None:
-        eng.load_weights(model.weights)
-        eng.set_evaluator(EVAL_NET)
-    else:
-        eng.set_evaluator(EVAL_HASH, int(evaluator[1]), int(evaluator[2]))
-    rng = random.Random(seed)
-    colors = [rng.random() >= 0.5 for _ in range(n_games)]       # colour of game i, drawn like selfplay.py:62
-    sp = LockstepSelfPlay(eng, n_games=lanes, sims=sims, noise=noise, inflight=threads)
-    t0 = time.perf_counter()
-    c0 = eng.counters()
-    sp.start(colors=colors[:lanes])
-    lane_game = list(range(lanes))                               # which game runs in which lane
-    next_game = lanes
-    records = [None] * n_games
-    # the engine's move lists hold 2,048 plies per game: a game that gets there is stored unfinished instead of
-    # failing the whole run (the fifty-move claim ends games long before that in practice)
-    cap = 2040 if max_moves is None else min(2040, 2 * max_moves)
-    steps = 0
-    while True:
-        again, parked = [], []
-        for lane, moves, result, color in sp.harvest(max_plies=cap):
-            records[lane_game[lane]] = (moves, color)
-            if next_game < n_games:
-                lane_game[lane] = next_game
-                again.append(lane)
-                next_game += 1
-            else:
-                parked.append(lane)
-        sp.restart(again, [colors[lane_game[g]] for g in again])   # one batch: games_set per run + one opening eval
-        sp.retire(parked)
-        if not sp.running().any():
-            break
-        sp.step()
-        steps += 1
-    if stats is not None:
-        c1 = eng.counters()
-        stats.update({"steps": steps, "moves": sp.moves_played, "seconds": time.perf_counter() - t0,
-                      "simulations": c1["simulations"] - c0["simulations"],
-                      "evaluations": c1["evaluations"] - c0["evaluations"], "lanes": lanes})
-    eng.close()
-    out = DatasetGame()
-    for moves, color in records:
-        gm = Game(player_color=color)
-        gm._sync(extra=[B.move_to_uci(m) for m in moves])
-        out.append(gm)
-    return out
+    The per-move host work is the numpy move policy only.  max_moves caps the agent moves of a game (it is then stored
+    unfinished, result None).  evaluator: None = the network with `model`'s weights; ("hash", seed, bits) = the
+    deterministic test evaluator.  stats: optional dict that receives steps / moves / simulations / seconds / lane
+    occupancy of the run."""
+    run = LockstepRun(model, n_games, sims=sims, lanes=lanes, noise=noise, device=device, seed=seed, max_moves=max_moves,
+                      threads=threads, evaluator=evaluator)
+    try:
+        while run.advance():
+            pass
+        if stats is not None:
+            stats.update(run.stats())
+    finally:
+        run.close()
+    return run.dataset()
 
 
 def main(argv=None):

@@ -164,6 +164,20 @@ int crl_games_get_host(crl_engine* e, int first, int n, uint64_t* boards_host, i
 int crl_games_set_active_host(crl_engine* e, int first, int n, const uint8_t* active_host);
 /* the moves of one game so far (DatasetGame / Game.get_history 'moves') */
 int crl_game_moves_host(crl_engine* e, int game, uint16_t* moves_host, int cap, int32_t* n_host);
+/* the batched forms of the calls above, one device round trip for many lanes (the lockstep driver's harvest / refill):
+ *   crl_games_restart_host : Game() in every listed lane (scattered lanes, all from the record start_host [9]) -- the
+ *                            `for game in range(games)` loop of selfplay.py:142-162 refilling a lane as its game ends
+ *   crl_games_moves_host   : Game.get_history()['moves'] (game.py:59-66) of the listed lanes: moves_host [n][cap],
+ *                            n_moves_host [n] (the true length, even where it exceeds cap)
+ *   crl_games_play_host    : Game.move (game.py:28-41) of one optional move per lane (moves_host [n_games], 0xFFFF =
+ *                            none); accepted_host [n_games] (may be NULL) = whether it was legal and played
+ *   crl_games_legal_host   : Game.get_legal_moves (game.py:43-57) of lanes first..first+n-1: legal_host [n][256],
+ *                            n_legal_host [n] */
+int crl_games_restart_host(crl_engine* e, const int32_t* lanes_host, int n, const uint64_t* start_host);
+int crl_games_moves_host(crl_engine* e, const int32_t* lanes_host, int n, uint16_t* moves_host, int cap,
+                         int32_t* n_moves_host);
+int crl_games_play_host(crl_engine* e, const uint16_t* moves_host, uint8_t* accepted_host);
+int crl_games_legal_host(crl_engine* e, int first, int n, uint16_t* legal_host, int32_t* n_legal_host);
 /* AgentDistributed.best_move(real_game=True) (agentdistributed.py:56-58): policy argmax over legal moves for
  * every game with mask_host[g] != 0 (NULL = all running games); writes picks_host [n_games] and plays them. */
 int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t* picks_host);

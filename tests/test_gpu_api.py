@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import chessrl_oracle as O
+from chessrl_b200 import boards as B
 
 pytestmark = pytest.mark.gpu
 chess = O.chess
@@ -279,3 +280,69 @@ def test_whole_selfplay_games_replay_under_the_oracle():
         assert og.get_result() == h["result"]
         finished += h["result"] is not None
     assert finished >= 8          # only a 2,040-ply game would be stored unfinished
+
+
+def test_policy_only_benchmark_loop_against_random_and_network_opponents(tmp_path):
+    """benchmark.py:59-143 on lockstep lanes: the agent moves by policy argmax (Agent.best_move(real_game=True)), the
+    opponent is a seeded random mover or a second network; every game replays under the oracle, move for move."""
+    from chessrl_b200 import benchmark
+    from chessrl_b200.agent import Agent
+    from chessrl_b200.game import Game
+    agent = Agent(True)
+    path = str(tmp_path / "model-0.h5")
+    agent.save(path)
+    games = benchmark.play_policy_games(agent, opponent="random", games=7, lanes=3, seed=5, max_plies=60)
+    assert len(games) == 7 and all(g is not None for g in games)
+    assert len({g["color"] for g in games}) == 2                       # both colours were drawn
+    for rec in games:
+        og = O.OGame()
+        g = Game()
+        for ply, m in enumerate(rec["moves"]):
+            agent_to_move = (ply % 2 == 0) == rec["color"]
+            if agent_to_move and ply < 6:                               # the agent's plies are its policy argmax
+                assert agent.best_move(g, real_game=True) == m
+            assert og.move(m), (ply, m)                                 # legal under the oracle
+            g.move(m)
+        assert rec["result"] == og.get_result()
+        assert rec["result"] is not None or len(rec["moves"]) >= 60
+    # network versus the same network: deterministic, so every game of one colour is the same game
+    twin = benchmark.play_policy_games(agent, opponent=agent, games=4, lanes=4, seed=1, max_plies=40)
+    assert len({tuple(g["moves"]) for g in twin}) == 1
+    g = Game()
+    for m in twin[0]["moves"][:8]:
+        assert agent.best_move(g, real_game=True) == m
+        g.move(m)
+    tally = benchmark.benchmark(str(tmp_path), workers=2, games=3, opponent="random", seed=2)
+    assert set(tally) == {"played", "won", "drawn"} and tally["played"] == 3
+    os.makedirs(str(tmp_path / "empty"))
+    assert benchmark.benchmark(str(tmp_path / "empty"), games=1) is None       # "Model not found" (benchmark.py:78-82)
+
+
+def test_batched_lane_calls_match_the_per_lane_ones():
+    """crl_games_restart_host / crl_games_moves_host / crl_games_play_host / crl_games_legal_host against the one-lane
+    calls they batch."""
+    from chessrl_b200.engine import Engine
+    e = Engine(max_games=6, max_nodes=4)
+    lines = [["e2e4", "e7e5"], ["d2d4"], [], ["g1f3", "g8f6", "c2c4"], ["e2e4", "c7c5", "g1f3"], ["b1c3"]]
+    e.games_set(np.tile(B.record_from_fen(), (6, 1)), [[B.uci_to_move(m) for m in l] for l in lines])
+    got = e.games_moves([5, 0, 3])
+    assert [[B.move_to_uci(m) for m in l] for l in got] == [lines[5], lines[0], lines[3]]
+    assert all(list(e.game_moves(g)) == [B.uci_to_move(m) for m in lines[g]] for g in range(6))
+    legal, cnt = e.games_legal(0, 6)
+    for g in range(6):
+        og = O.OGame()
+        for m in lines[g]:
+            og.move(m)
+        assert [B.move_to_uci(m) for m in legal[g, :cnt[g]]] == og.get_legal_moves()
+    mv = np.full(6, B.MOVE_NONE, dtype=np.uint16)
+    mv[0], mv[1], mv[2] = B.uci_to_move("g1f3"), B.uci_to_move("d2d4"), B.uci_to_move("e2e4")     # lane 1: illegal now
+    acc = e.games_play(mv)
+    assert list(acc) == [True, False, True, False, False, False]
+    _, plies, _ = e.games_get(0, 6)
+    assert list(plies) == [3, 1, 1, 3, 3, 1]
+    e.games_restart([4, 1])
+    _, plies, results = e.games_get(0, 6)
+    assert list(plies) == [3, 0, 1, 3, 0, 1] and (results == B.RESULT_NONE).all()
+    rec, _, _ = e.games_get(0, 6)
+    assert (rec[1] == B.record_from_fen()).all() and (rec[4] == B.record_from_fen()).all()
+    e.close()
