@@ -270,6 +270,34 @@ def test_rules_on_unreachable_random_positions(engine1):
     assert k == kids.shape[1]
 
 
+def test_movegen_order_invariants_on_device(engine1):
+    """k_movegen's lists against the structural order rules of python-chess (tests/move_order_rules.py: class order
+    1-6, from / to descending, q r b n, king evasions first) -- a validator that generates no move itself -- over
+    4,000 fuzzed positions and the children of 300 of them; the in-check flag comes from the kernel as well."""
+    import move_order_rules
+    rng = random.Random(77)
+    cases = [position_fuzz.random_fen(rng)[0] for _ in range(4000)]
+    recs = np.stack([B.record_from_fen(fen) for fen in cases])
+    t = engine1.boards_to_device(recs)
+    kids, _ = engine1.expand_frontier(t[:, :300].contiguous())
+    recs = np.concatenate([recs, engine1.boards_to_host(kids)])
+    t = engine1.boards_to_device(recs)
+    mv, cn, fl = engine1.movegen(t)
+    moves = mv.cpu().numpy().view(np.uint16)
+    counts, flags = cn.cpu().numpy(), fl.cpu().numpy()
+    seen = {"check": 0, "castle": 0, "promo": 0, "ep": 0}
+    for i in range(recs.shape[0]):
+        words = [int(m) for m in moves[i, :counts[i]]]
+        bad = move_order_rules.violations(recs[i], words, bool(flags[i] & 1))
+        assert not bad, (B.fen_from_record(recs[i]), bad)
+        cls = [move_order_rules.classify(recs[i], w) for w in words]
+        seen["check"] += int(flags[i] & 1)
+        seen["castle"] += any(c[0] == 2 for c in cls)
+        seen["promo"] += any(c[3] >= 0 for c in cls)
+        seen["ep"] += any(c[0] == 6 for c in cls)
+    assert min(seen.values()) >= 100, seen
+
+
 @pytest.mark.parametrize("mode", ["5", "6"])
 def test_perft_root_two_ply_pass(mode, monkeypatch):
     """The optional fused pass over the last two plies (CRL_PERFT_PAIR=5 / 6, read at engine creation): same totals as

@@ -162,3 +162,133 @@ def test_golden_rules(golden_dir):
                 n += 1
         assert g.get_result() == c["final_result"]
     assert n > 500
+
+
+# ---- vectors from outside this repository (tests/pychess_kats.py: python-chess README / docs, and its test-suite) ------
+import random  # noqa: E402
+
+import move_order_rules  # noqa: E402
+import position_fuzz  # noqa: E402
+import pychess_kats as K  # noqa: E402
+from chessrl_b200 import boards as B  # noqa: E402
+
+
+def test_readme_scholars_mate_walkthrough():
+    b = chess.Board()
+    assert [m.uci() for m in b.legal_moves] == K.README_START_LEGAL_MOVES
+    assert b.legal_moves.count() == 20 and bool(b.legal_moves) and chess.Move.from_uci("g1f3") in b.legal_moves
+    for m in K.README_SCHOLARS_MATE:
+        mv = chess.Move.from_uci(m)
+        assert mv in b.legal_moves
+        b.push(mv)
+    assert b.fen() == K.README_SCHOLARS_MATE_FEN
+    for name, want in K.README_SCHOLARS_MATE_FLAGS.items():
+        assert getattr(b, name)() is want, name
+    assert b.halfmove_clock == K.README_SCHOLARS_MATE_HALFMOVE_CLOCK
+    assert b.is_attacked_by(chess.WHITE, 60) is K.README_ATTACKED_E8_BY_WHITE
+    assert b.attackers_mask(chess.WHITE, 21) == K.README_ATTACKERS_OF_F3_BY_WHITE
+    assert b.result() == "1-0" and O.OGame(board=b).get_result() == 1
+    assert b.pop().uci() == "h5f7" and not b.is_checkmate()               # "make and unmake moves"
+    r = chess.Board(K.README_FEN_ROUND_TRIP)
+    assert r.fen() == K.README_FEN_ROUND_TRIP and r.piece_type_at(34) == chess.KING and not r.occupied_co[chess.WHITE] & (1 << 34)
+
+
+def test_squareset_semantics_used_by_netencoder():
+    s = chess.SquareSet(K.SQUARESET_DOC_MASK)
+    assert len(s) == 9 and bool(s) and 1 in s and list(s) == K.SQUARESET_DOC_LIST
+    bools = s.tolist()
+    assert len(bools) == 64 and [i for i, x in enumerate(bools) if x] == K.SQUARESET_DOC_LIST
+    assert list(s.mirror()) == [0, 56, 57, 58, 59, 60, 61, 62, 63]        # vertical mirror: rank 1 <-> rank 8
+
+
+@pytest.mark.parametrize("fen,white,black", K.INSUFFICIENT)
+def test_suite_insufficient_material_per_colour(fen, white, black):
+    b = chess.Board(fen)
+    assert b.has_insufficient_material(chess.WHITE) is white and b.has_insufficient_material(chess.BLACK) is black
+    assert b.is_insufficient_material() is (white and black)
+
+
+def test_suite_fivefold_repetition_need_not_be_consecutive():
+    b = chess.Board(K.FIVEFOLD_FEN)
+    g = O.OGame(board=chess.Board(K.FIVEFOLD_FEN))
+    for cycle in range(4):
+        for m in K.FIVEFOLD_CYCLE:
+            assert not b.is_fivefold_repetition() and not b.is_game_over() and g.get_result() is None
+            b.push(chess.Move.from_uci(m))
+            assert g.move(m)
+    assert b.is_fivefold_repetition() and b.is_game_over() and g.get_result() == 0
+    assert b.is_repetition(3)
+    for m in K.FIVEFOLD_DETOUR:
+        b.push(chess.Move.from_uci(m))
+        assert not b.is_fivefold_repetition() and not b.is_game_over()
+    b.push(chess.Move.from_uci(K.FIVEFOLD_RETURN))
+    assert b.is_fivefold_repetition() and b.fen().split()[0] == K.FIVEFOLD_FEN.split()[0]
+
+
+@pytest.mark.parametrize("fen,claim,seventyfive", K.FIFTY_MOVES)
+def test_suite_fifty_move_claim(fen, claim, seventyfive):
+    b = chess.Board(fen)
+    assert b.can_claim_fifty_moves() is claim and b.is_seventyfive_moves() is seventyfive
+    res = O.OGame(board=chess.Board(fen)).get_result()
+    if claim:
+        assert res == 0                                                  # game.py:95-96: the claim ends the game
+    elif b.is_checkmate():
+        assert res in (1, -1)
+    elif b.is_stalemate():
+        assert res == 0
+
+
+def test_version_switches_stay_at_0_28_3():
+    assert chess.FIFTY_MOVE_CLAIM_LOOKAHEAD is False and chess.REPETITION_STOPS_ON_LEGAL_EP is False
+
+
+def _order_violations(board):
+    rec = B.record_from_fen(board.fen())                                  # bitboards only: the validator generates nothing
+    words = [B.uci_to_move(m.uci()) for m in board.legal_moves]
+    return move_order_rules.violations(rec, words, board.is_check())
+
+
+def test_move_order_invariants_on_fuzzed_positions_and_games():
+    """Class order 1-6, from / to squares descending, q r b n, king evasions first: the structural rules of
+    SURVEY.md 8c as an independent validator over positions with promoted material, checks, castling and ep."""
+    rng = random.Random(2024)
+    n_check = n_castle = n_promo = n_ep = 0
+    for _ in range(1500):
+        fen, b = position_fuzz.random_fen(rng)
+        bad = _order_violations(b)
+        assert not bad, (fen, bad)
+        ms = [m.uci() for m in b.legal_moves]
+        n_check += b.is_check()
+        n_castle += any(m in ("e1g1", "e1c1", "e8g8", "e8c8") and b.piece_type_at(chess.Move.from_uci(m).from_square) == chess.KING for m in ms)
+        n_promo += any(len(m) == 5 for m in ms)
+        n_ep += b.has_legal_en_passant()
+    assert min(n_check, n_castle, n_promo, n_ep) >= 25, (n_check, n_castle, n_promo, n_ep)
+    for fen, _ in PERFT + [(f, None) for f in perft_kats.MAX_MOVES]:
+        assert not _order_violations(chess.Board(fen))
+    b = chess.Board()
+    for _ in range(300):                                                  # along a random game from the start
+        ms = list(b.legal_moves)
+        if not ms:
+            break
+        assert not _order_violations(b)
+        b.push(rng.choice(ms))
+
+
+def test_move_order_validator_rejects_wrong_orders():
+    """The validator bites: swapping two moves, or reordering a promotion group, is reported."""
+    b = chess.Board(KIWI)
+    rec = B.record_from_fen(KIWI)
+    words = [B.uci_to_move(m.uci()) for m in b.legal_moves]
+    assert not move_order_rules.violations(rec, words, False)
+    for i in range(len(words) - 1):
+        sw = list(words)
+        sw[i], sw[i + 1] = sw[i + 1], sw[i]
+        assert move_order_rules.violations(rec, sw, False), i
+    p = chess.Board("1n2k3/P7/8/8/8/8/8/4K3 w - - 0 1")
+    words = [B.uci_to_move(m.uci()) for m in p.legal_moves]
+    rec = B.record_from_fen(p.fen())
+    assert not move_order_rules.violations(rec, words, False)
+    qs = [i for i, w in enumerate(words) if (w >> 12) == 4]
+    sw = list(words)
+    sw[qs[0]], sw[qs[0] + 3] = sw[qs[0] + 3], sw[qs[0]]                   # n, r, b, q instead of q, r, b, n
+    assert move_order_rules.violations(rec, sw, False)
