@@ -8,7 +8,12 @@
 //     with coalesced loads, score them in float64 exactly as Node.get_value does, and reduce to the FIRST
 //     maximum with shuffles (np.argmax semantics).  Lane 0 then pops the last unexpanded action and creates
 //     the child.
-//   * k_reply / k_finalize : one thread per batch row / per game (movegen + make-move are per-thread code).
+//   * the rule code of an expansion (make-move, legal moves, transposition key, Game.get_result) is per-THREAD code,
+//     as in k_movegen.  k_select_expand and k_reply therefore work in two phases inside a block of TREE_GAMES games:
+//     phase 1, one warp per game / row -- the cooperative child scans (select) or the legal-masked policy gather and
+//     its first-maximum reduction (reply); __syncthreads(); phase 2, the block's games packed ONE THREAD EACH into the
+//     first warp for the rule code.  (With lane 0 of every warp doing it, 31 of 32 lanes idled through ~3,000
+//     instructions per game: 4,096 games cost 12 M warp instructions instead of 0.4 M.)
 // With one in-flight simulation per game (the reference's deterministic threads=1 schedule) no atomics are
 // needed on the statistics; the only atomics are the batch-compaction counters.
 #include "engine.cuh"
@@ -18,6 +23,8 @@
 namespace crl {
 
 static constexpr int TREE_BLOCK = 128;
+static constexpr int TREE_GAMES = 8;                    // games (or batch rows) per block of the two-phase kernels
+static constexpr int TREE_THREADS = TREE_GAMES * 32;
 
 __device__ __forceinline__ bool game_running(const Pools& P, int g) {
   return P.g_active[g] && P.g_result[g] == RESULT_NONE;
@@ -54,22 +61,37 @@ struct WarpScan {
   }
 };
 
-__global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= P.G) return;
-  if (!game_running(P, g)) {
-    if (lane == 0) P.s_kind[g] = KIND_IDLE;
-    return;
+__global__ void __launch_bounds__(TREE_THREADS) k_select_expand(Pools P) {
+  __shared__ int s_todo[TREE_GAMES];                    // node to expand per game of the block, -1 = nothing to expand
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    // phase 1: SelfPlayTree.select's descent (mctree.py:216-225), one warp per game
+    const int g = blockIdx.x * TREE_GAMES + w;
+    int todo = -1;
+    if (g < P.G) {
+      if (!game_running(P, g)) {
+        if (lane == 0) P.s_kind[g] = KIND_IDLE;
+      } else {
+        int node, term;
+        select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
+        if (term) {
+          if (lane == 0) {
+            P.s_node[g] = node;
+            P.s_kind[g] = KIND_TERMINAL;
+          }
+        } else {
+          todo = node;
+        }
+      }
+    }
+    if (lane == 0) s_todo[w] = todo;
   }
-  int node, term;
-  select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
-  if (lane != 0) return;
-  if (term) {
-    P.s_node[g] = node;
-    P.s_kind[g] = KIND_TERMINAL;
-    return;
-  }
+  __syncthreads();
+  // phase 2: SelfPlayTree.expand's first half (mctree.py:241-244), one thread per game
+  if (threadIdx.x >= TREE_GAMES) return;
+  const int g = blockIdx.x * TREE_GAMES + threadIdx.x;
+  const int node = s_todo[threadIdx.x];
+  if (g >= P.G || node < 0) return;
   int child;
   int kind = expand_child(P, g, g, node, &child);
   P.s_node[g] = child;
@@ -169,43 +191,51 @@ __global__ void __launch_bounds__(256) k_wave_left(Pools P, int* out) {
 }
 
 // rows of batch A (positions after our move) -> opponent reply, node state, batch B.
-// One WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
-// (agentdistributed.py:56-58); lane 0 then plays the reply and builds the node.
-__global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __restrict__ policy,
-                                                      const int16_t* __restrict__ label_of, int* list_b,
-                                                      int* n_b) {
-  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+// Phase 1, one WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
+// (agentdistributed.py:56-58).  Phase 2, one THREAD per row: play the reply and build the node (mctree.py:245-249).
+__global__ void __launch_bounds__(TREE_THREADS) k_reply(Pools P, const float* __restrict__ policy,
+                                                        const int16_t* __restrict__ label_of, int* list_b,
+                                                        int* n_b) {
+  __shared__ int s_pick[TREE_GAMES];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_a = *P.eval_n;
-  if (r == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
+  {
+    const int r = blockIdx.x * TREE_GAMES + w;
+    if (r < n_a) {
+      const int slot = P.eval_list[r];
+      const float* row = policy + (long long)r * CRL_N_LABELS;
+      const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
+      const int n1 = P.s_nmoves[slot];
+      float best_p = -CUDART_INF_F;
+      int best_i = 0x7fffffff;
+      for (int i = lane; i < n1; i += 32) {
+        const u16 m = moves1[i];
+        const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+        if (p > best_p) {
+          best_p = p;
+          best_i = i;
+        }
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float op = __shfl_xor_sync(0xffffffffu, best_p, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+        if (op > best_p || (op == best_p && oi < best_i)) {
+          best_p = op;
+          best_i = oi;
+        }
+      }
+      if (lane == 0) s_pick[w] = best_i;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x >= TREE_GAMES) return;
+  const int r = blockIdx.x * TREE_GAMES + threadIdx.x;
   if (r >= n_a) return;
   const int slot = P.eval_list[r];
   const int g = slot / P.K;
-  const int child = P.s_node[slot];
-  const float* row = policy + (long long)r * CRL_N_LABELS;
-  const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
-  const int n1 = P.s_nmoves[slot];
-  float best_p = -CUDART_INF_F;
-  int best_i = 0x7fffffff;
-  for (int i = lane; i < n1; i += 32) {
-    const u16 m = moves1[i];
-    const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
-    if (p > best_p) {
-      best_p = p;
-      best_i = i;
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    const float op = __shfl_xor_sync(0xffffffffu, best_p, off);
-    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-    if (op > best_p || (op == best_p && oi < best_i)) {
-      best_p = op;
-      best_i = oi;
-    }
-  }
-  if (lane != 0) return;
-  int kind = reply_child(P, g, slot, child, row, label_of, best_i);
+  int kind = reply_child(P, g, slot, P.s_node[slot], policy + (long long)r * CRL_N_LABELS, label_of, s_pick[threadIdx.x]);
   P.s_kind[slot] = kind;
   if (kind == KIND_EVAL_LEAF) {
     int rb = atomicAdd(n_b, 1);
@@ -441,15 +471,15 @@ static int one_simulation(crl_engine_impl* e) {
   e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
-    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
+    k_select_expand<<<div_up(e->G, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P);
     CRL_CUDA(cudaGetLastError());
   }
   int rc = launch_eval_batch(e, 1);
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
-                                                                                   e->d_list[1], e->d_n + 1);
+    k_reply<<<div_up(e->G, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, e->d_list[1],
+                                                                      e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);
@@ -479,8 +509,8 @@ static int one_wave(crl_engine_impl* e, int K) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up((long long)e->cur_rows * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
-                                                                                         e->d_list[1], e->d_n + 1);
+    k_reply<<<div_up(e->cur_rows, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                             e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);

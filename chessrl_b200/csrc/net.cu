@@ -505,6 +505,27 @@ __device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* 
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same loads with an L2 eviction-priority hint (createpolicy encodings, as CUTLASS's TMA::CacheHintSm90)
+static constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+static constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+static constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void tma2_load_4d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                  int c2, int c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                                  uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
 __device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                            uint32_t accumulate) {
   asm volatile(
@@ -773,6 +794,9 @@ struct TrunkParams {
   float* vf_out;
   __nv_bfloat16* dbg_out;   // test tap (crl_debug_tower): layer dbg_layer's output [boards][64][256], else null
   int dbg_layer;
+  // L2 eviction priorities of the v4 tower's TMA loads: the planes are read once (evict first), the weights are re-read
+  // by every CTA pair for every group (evict last), the activation scratch keeps the default
+  uint64_t hint_planes, hint_weights;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
@@ -1104,7 +1128,8 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
             // coordinates (channel, x, board, y): the box {64, 10, 2, 10} starts one pixel outside the board.
             // The planes are indexed by board, the activation scratch by this pair's slot.
             const int b0 = (ld.map_in == 0 ? tile * 4 : pair * 8 + X * 4) + (int)rank * 2;
-            tma2_load_4d(smem_a + as * T4_A_SLOT, map_a, &a_full[as], kc * BLOCK_K, -1, b0, -1);
+            tma2_load_4d_hint(smem_a + as * T4_A_SLOT, map_a, &a_full[as], kc * BLOCK_K, -1, b0, -1,
+                              ld.map_in == 0 ? p.hint_planes : L2_EVICT_NORMAL);
             if (rank != 0) mbar_arrive_remote(&a_full[as], 0);
             if (++as == T4_NA) {
               as = 0;
@@ -1113,7 +1138,8 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[bs], bphase ^ 1);
               if (rank == 0) mbar_arrive_expect_tx(&b_full[bs], 2 * T4_B_BYTES);
-              tma2_load_2d(smem_b + bs * T4_B_BYTES, map_w, &b_full[bs], (tap * ld.k_chunks + kc) * BLOCK_K, (int)rank * 128);
+              tma2_load_2d_hint(smem_b + bs * T4_B_BYTES, map_w, &b_full[bs], (tap * ld.k_chunks + kc) * BLOCK_K,
+                                (int)rank * 128, p.hint_weights);
               if (rank != 0) mbar_arrive_remote(&b_full[bs], 0);
               if (++bs == T4_NB) {
                 bs = 0;
@@ -1388,6 +1414,7 @@ struct NetWeights {
   int t4_ring = 0;                          // index into the instantiated (image slots, weight stages) pairs
   __nv_bfloat16* act4[2] = {nullptr, nullptr};  // [n_sms/2 pairs x 8 boards][64][256]: ping-pong scratch by CTA-pair slot
   int act4_rows = 0;
+  bool l2_hints = true;                     // CRL_T4_L2_HINTS=0 turns the eviction-priority hints off (A/B)
   CUtensorMap map_act4[2];
   CUtensorMap map_planes4;
   CUtensorMap* d_maps4 = nullptr;
@@ -1535,6 +1562,8 @@ int net_create(crl_engine_impl* e) {
     const char* r = getenv("CRL_T4_RING");   // tuning knob: 0 = 3/7 (default), 1 = 3/8, 2 = 2/9, 3 = 2/10
     nw->t4_ring = r ? atoi(r) : 0;
     if (nw->t4_ring < 0 || nw->t4_ring > 3) nw->t4_ring = 0;
+    const char* h = getenv("CRL_T4_L2_HINTS");
+    nw->l2_hints = !(h && h[0] == '0');
   }
   {
     // tensor-map table + layer table for the whole-tower kernel
@@ -1833,6 +1862,8 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     tp.vf_out = nw->vf;
     tp.dbg_out = dbg_out;
     tp.dbg_layer = dbg_layer;
+    tp.hint_planes = nw->l2_hints ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    tp.hint_weights = nw->l2_hints ? L2_EVICT_LAST : L2_EVICT_NORMAL;
     int groups = ((n_host + 3) / 4 + 1) / 2;
     int pairs = groups < nw->n_sms / 2 ? groups : nw->n_sms / 2;
     if (pairs < 1) pairs = 1;
