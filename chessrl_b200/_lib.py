@@ -44,6 +44,7 @@ SIGNATURES = {
     "crl_last_error": (ctypes.c_char_p, []),
     "crl_version": (ctypes.c_int, []),
     "crl_movegen": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, vp, vp]),
+    "crl_debug_movegen_warp": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, vp, vp]),
     "crl_make_moves": (ctypes.c_int, [vp, vp, ctypes.c_int, vp]),
     "crl_perft": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "crl_perft_root_host": (ctypes.c_int, [vp, c_u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_u64p, c_i64p, c_i32p]),

@@ -349,6 +349,15 @@ int crl_movegen(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* move
   }
   return launch_movegen(e, boards_dev, n, moves_dev, counts_dev, flags_dev);
 }
+int crl_debug_movegen_warp(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* moves_dev, int32_t* counts_dev,
+                           uint8_t* flags_dev) {
+  CHECK_ENGINE(e);
+  if (n < 0 || (n > 0 && (!boards_dev || !moves_dev || !counts_dev))) {
+    set_error("crl_debug_movegen_warp: bad arguments");
+    return CRL_EINVAL;
+  }
+  return launch_movegen_warp(e, boards_dev, n, moves_dev, counts_dev, flags_dev);
+}
 int crl_make_moves(crl_engine* e, uint64_t* boards_dev, int n, const uint16_t* moves_dev) {
   CHECK_ENGINE(e);
   if (n < 0 || (n > 0 && (!boards_dev || !moves_dev))) {
@@ -399,13 +408,13 @@ int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int
       e->perft_cap = cap;
     }
     const long long stride = e->perft_cap;
-    // the root record goes to column 0 of buffer 0 (structure of arrays: word k at [k * stride])
-    CRL_CUDA(cudaMemcpy2DAsync(e->perft_buf[0], (size_t)stride * 8, root_host, 8, 8, 9, cudaMemcpyHostToDevice, e->stream));
-    int rc = launch_perft_root(e, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk, min_frontier,
-                               e->perft_pair);
+    // the root record travels as a kernel parameter (no copy), the control block is initialised on the device
+    int rc = launch_perft_root(e, root_host, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk,
+                               min_frontier, e->perft_pair);
     if (rc) return rc;
-    unsigned long long ctl[8];
-    CRL_CUDA(cudaMemcpyAsync(ctl, e->perft_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e->stream));
+    if ((rc = ensure_stage(e, 64))) return rc;
+    unsigned long long* ctl = (unsigned long long*)e->h_stage;          // pinned: the read-back is one async copy
+    CRL_CUDA(cudaMemcpyAsync(ctl, e->perft_ctl, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CRL_CUDA(cudaStreamSynchronize(e->stream));
     if (ctl[3] == 0) {
       *total_host = depth == 0 ? 1 : ctl[4];

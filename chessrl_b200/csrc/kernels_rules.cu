@@ -4,6 +4,7 @@
 //
 // Replaces python-chess behind game.Game.get_legal_moves / Game.move (game.py:28-57); see chess_core.cuh.
 #include "engine.cuh"
+#include "warp_gen.cuh"
 
 namespace crl {
 
@@ -76,6 +77,25 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_movegen(const u64* __restrict__
       const u32 a = *reinterpret_cast<const u32*>(src + k), b2 = *reinterpret_cast<const u32*>(src + k + 2);
       *reinterpret_cast<uint2*>(dst + k) = make_uint2(a, b2);
     }
+  }
+}
+
+// test hook (crl_debug_movegen_warp): the warp-cooperative generator the tree kernels and the small perft plies use,
+// one warp per board, same outputs as k_movegen
+__global__ void __launch_bounds__(RULES_BLOCK) k_movegen_warp(const u64* __restrict__ boards, int n, u16* __restrict__ moves,
+                                                              int* __restrict__ counts, u8* __restrict__ flags) {
+  __shared__ u16 s_gen[RULES_BLOCK / 32][MAX_MOVES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * (RULES_BLOCK / 32) + warp;
+  if (i >= n) return;
+  const Board b = load_soa(boards, n, i);
+  int chk, epl;
+  const int cnt = warp_generate_legal(b, s_gen[warp], lane, &chk, &epl);
+  __syncwarp();
+  for (int k = lane; k < cnt; k += 32) moves[i * MAX_MOVES + k] = s_gen[warp][k];
+  if (lane == 0) {
+    counts[i] = cnt;
+    if (flags) flags[i] = (u8)((chk ? 1 : 0) | (epl ? 2 : 0));
   }
 }
 
@@ -165,7 +185,8 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ b
 // more than one lane's stack can walk; never beyond depth-1 plies (the last ply is always counted by the walk).
 // With `pair` the last TWO plies belong to k_perft_pair (the last-but-one ply is expanded and counted in one pass,
 // never stored), so breadth-first expansion stops one ply earlier.
-__device__ __forceinline__ bool bfs_active(const unsigned long long* ctl, long long min_frontier, int depth, int pair) {
+template <class CtlPtr>
+__device__ __forceinline__ bool bfs_active(CtlPtr ctl, long long min_frontier, int depth, int pair) {
   const int plies = (int)ctl[2];
   const int last = (pair && depth >= 2) ? depth - 2 : depth - 1;
   if (ctl[3] || plies >= last) return false;
@@ -205,20 +226,17 @@ struct BfsSink {
   }
 };
 
-__global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
-                                                         unsigned long long* __restrict__ ctl, long long min_frontier,
-                                                         int depth, int pair) {
-  __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
-  __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
-  __shared__ int s_pre[RULES_BLOCK / 32][33];
-  if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid
-  const long long n = (long long)ctl[0];
-  const int plies = (int)ctl[2];
-  const u64* in = (plies & 1) ? buf1 : buf0;
-  u64* out = (plies & 1) ? buf0 : buf1;
+typedef u64 (*BfsBoards)[9][32];
+typedef u16 (*BfsMoves)[32][BFS_CAP];
+typedef int (*BfsPre)[33];
+
+// one breadth-first ply over parents i0, i0 + istride, ... of `in` (n boards) for the calling thread's warp
+__device__ __forceinline__ void bfs_expand(const u64* __restrict__ in, u64* __restrict__ out, long long cap, long long n,
+                                           unsigned long long* __restrict__ ctl, long long i0, long long istride,
+                                           BfsBoards s_board, BfsMoves s_moves, BfsPre s_pre) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_pad = (n + 31) & ~31LL;                            // whole warps stay together
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x) {
+  for (long long i = i0; i < n_pad; i += istride) {
     // ---- phase 1: one parent per lane ----
     u16 spill[MAX_MOVES - BFS_CAP];
     BfsSink sink{s_moves[warp][lane], spill, 0};
@@ -278,11 +296,101 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0,
     __syncwarp();                                                      // the rows are reused by the next round
   }
 }
-__global__ void k_bfs_commit(unsigned long long* __restrict__ ctl, long long min_frontier, int depth, int pair) {
-  if (!bfs_active(ctl, min_frontier, depth, pair)) return;
+
+// The same ply with ONE WARP PER PARENT (warp_gen.cuh) for small frontiers: a thread-per-parent ply costs one scalar
+// move generation of latency (~30 us) however few parents there are; 32 lanes on one board bring that to a few us,
+// and the children of a parent are made by consecutive lanes, so their records are stored coalesced.
+//   gen = this warp's shared-memory move row (>= MAX_MOVES entries); parents w0, w0 + wstride, ...
+__device__ __forceinline__ void bfs_expand_warp(const u64* __restrict__ in, u64* __restrict__ out, long long cap, long long n,
+                                                unsigned long long* __restrict__ ctl, long long w0, long long wstride,
+                                                u16* gen) {
+  const int lane = threadIdx.x & 31;
+  for (long long i = w0; i < n; i += wstride) {
+    const Board b = load_soa(in, cap, i);                              // same address in every lane: one broadcast load
+    int chk, epl;
+    const int cnt = warp_generate_legal(b, gen, lane, &chk, &epl);
+    unsigned long long base = 0;
+    if (lane == 0 && cnt) base = atomicAdd(&ctl[1], (unsigned long long)cnt);
+    base = __shfl_sync(0xffffffffu, base, 0);                          // (also orders the row's writes before its reads)
+    __syncwarp();
+    if (base + cnt > (unsigned long long)cap) {
+      if (lane == 0) ctl[3] = 1;
+    } else {
+      for (int j = lane; j < cnt; j += 32) {
+        Board c = b;
+        make_move(c, gen[j]);
+        store_soa(out, cap, (long long)base + j, c);
+      }
+    }
+    __syncwarp();                                                      // the row is reused by the next parent
+  }
+}
+static constexpr long long BFS_WARP_MAX = 12288;   // frontiers up to this size expand one warp per parent
+
+// the frontier just written becomes the current one
+__device__ __forceinline__ void bfs_commit(unsigned long long* ctl) {
   ctl[0] = ctl[1];
   ctl[1] = 0;
   ctl[2] += 1;
+}
+
+// One grid-wide ply.  The LAST block to finish commits the ply (ctl[6] counts finished blocks), so a ply is one launch.
+__global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
+                                                         unsigned long long* __restrict__ ctl, long long min_frontier,
+                                                         int depth, int pair) {
+  __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
+  __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
+  __shared__ int s_pre[RULES_BLOCK / 32][33];
+  if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid: nobody commits before
+  const long long n = (long long)ctl[0];                              // every block has read the control block
+  const int plies = (int)ctl[2];
+  const u64* in = (plies & 1) ? buf1 : buf0;
+  u64* out = (plies & 1) ? buf0 : buf1;
+  if (n <= BFS_WARP_MAX)
+    bfs_expand_warp(in, out, cap, n, ctl, (long long)blockIdx.x * (RULES_BLOCK / 32) + (threadIdx.x >> 5),
+                    (long long)gridDim.x * (RULES_BLOCK / 32), &s_moves[threadIdx.x >> 5][0][0]);
+  else
+    bfs_expand(in, out, cap, n, ctl, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x,
+               s_board, s_moves, s_pre);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&ctl[6], 1ull) + 1 == (unsigned long long)gridDim.x) {
+      ctl[6] = 0;
+      bfs_commit(ctl);
+    }
+  }
+}
+
+// The root and the first plies in ONE block (1 -> 20 -> 400 boards from the start position): the root record arrives as
+// a kernel parameter, the control block is initialised here, and up to `n_plies` plies run back to back with a block
+// barrier in between -- no copies, no memset, no launch per tiny ply.
+struct RootRecord {
+  u64 w[9];
+};
+static constexpr int FIRST_THREADS = 512;          // 16 warps: the 20 children of the start position in two rounds
+static constexpr long long FIRST_MAX = 96;         // k_bfs_first keeps going while the frontier is at most this large
+__global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u64* __restrict__ buf0, u64* __restrict__ buf1,
+                                                             long long cap, unsigned long long* __restrict__ ctl,
+                                                             long long min_frontier, int depth, int pair, int n_plies) {
+  __shared__ u16 s_gen[FIRST_THREADS / 32][MAX_MOVES];
+  if (threadIdx.x < 8) ctl[threadIdx.x] = threadIdx.x == 0 ? 1ull : 0ull;
+  if (threadIdx.x < 9) buf0[(long long)threadIdx.x * cap] = root.w[threadIdx.x];     // column 0 of the SoA buffer
+  __syncthreads();
+  const volatile unsigned long long* vctl = ctl;
+  for (int ply = 0; ply < n_plies; ++ply) {
+    if (!bfs_active(vctl, min_frontier, depth, pair)) break;          // uniform: same control block for every thread
+    const long long n = (long long)vctl[0];
+    if (n > FIRST_MAX) break;                                          // the grid-wide ply kernels take over
+    const int plies = (int)vctl[2];
+    const u64* in = (plies & 1) ? buf1 : buf0;
+    u64* out = (plies & 1) ? buf0 : buf1;
+    __syncthreads();
+    bfs_expand_warp(in, out, cap, n, ctl, threadIdx.x >> 5, FIRST_THREADS / 32, s_gen[threadIdx.x >> 5]);
+    __syncthreads();
+    if (threadIdx.x == 0) bfs_commit(ctl);
+    __syncthreads();
+  }
 }
 __global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
                                                             long long cap, unsigned long long* __restrict__ ctl, int depth,
@@ -449,6 +557,13 @@ int launch_movegen(crl_engine_impl* e, const u64* boards, int n, u16* moves, int
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }
+int launch_movegen_warp(crl_engine_impl* e, const u64* boards, int n, u16* moves, int* counts, u8* flags) {
+  if (n <= 0) return CRL_OK;
+  LaunchScope ls(e, KC_MOVEGEN);
+  k_movegen_warp<<<div_up(n, RULES_BLOCK / 32), RULES_BLOCK, 0, e->stream>>>(boards, n, moves, counts, flags);
+  CRL_CUDA(cudaGetLastError());
+  return CRL_OK;
+}
 int launch_make(crl_engine_impl* e, u64* boards, int n, const u16* moves) {
   if (n <= 0) return CRL_OK;
   LaunchScope ls(e, KC_MOVEGEN);
@@ -467,27 +582,33 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }
-// enqueues the whole device-driven perft of the root record already stored at buf0[k*cap] (k = 0..8); ctl is zeroed here
-int launch_perft_root(crl_engine_impl* e, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl, int depth, int bulk,
-                      long long min_frontier, int pair) {
+// enqueues the whole device-driven perft of `root` (AoS record, host): the first kernel stores it and initialises ctl
+int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl,
+                      int depth, int bulk, long long min_frontier, int pair) {
   if (depth < 0 || depth > 64) {
     set_error("crl_perft_root_host: depth %d is not supported", depth);
     return CRL_EINVAL;
   }
-  CRL_CUDA(cudaMemsetAsync(ctl, 0, 8 * sizeof(unsigned long long), e->stream));
-  const unsigned long long one = 1;
-  CRL_CUDA(cudaMemcpyAsync(ctl, &one, sizeof(one), cudaMemcpyHostToDevice, e->stream));
   if (depth < 2) pair = 0;
   const int max_plies = depth - 1 - (pair ? 1 : 0) > 0 ? depth - 1 - (pair ? 1 : 0) : 0;
   const int max_grid = 148 * 12;
-  long long bound = 1;
-  for (int ply = 0; ply < max_plies; ++ply) {
-    // boards that can exist at this ply: <= 218^ply and, once the frontier is large enough, expansion stops
-    const int grid = (int)(div_up(bound, RULES_BLOCK) < max_grid ? div_up(bound, RULES_BLOCK) : max_grid);
+  // the first kernel always expands the root (ply 1) and goes on while the frontier stays tiny; ply 2 is enqueued as a
+  // grid ply as well (a no-op if the first kernel already did it -- it cannot be known here) so no ply is ever skipped
+  const int first_plies = max_plies < 2 ? max_plies : 2;
+  RootRecord rr;
+  for (int k = 0; k < 9; ++k) rr.w[k] = root[k];
+  {
+    LaunchScope ls(e, KC_MOVEGEN);
+    k_bfs_first<<<1, FIRST_THREADS, 0, e->stream>>>(rr, buf0, buf1, cap, ctl, min_frontier, depth, pair, first_plies);
+    CRL_CUDA(cudaGetLastError());
+  }
+  // How many boards a ply holds is only known on the device (and whether the first kernel ran one ply or two), so
+  // every grid ply gets the full grid: blocks without work leave after reading the control block.
+  long long bound = 218 < cap ? 218 : cap;
+  for (int ply = 1; ply < max_plies; ++ply) {
     {
-      LaunchScope ls(e, KC_MOVEGEN, 2);
-      k_bfs_ply<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair);
-      k_bfs_commit<<<1, 1, 0, e->stream>>>(ctl, min_frontier, depth, pair);
+      LaunchScope ls(e, KC_MOVEGEN);
+      k_bfs_ply<<<max_grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair);
       CRL_CUDA(cudaGetLastError());
     }
     bound = bound * 218 < cap ? bound * 218 : cap;

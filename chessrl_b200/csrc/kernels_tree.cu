@@ -8,23 +8,23 @@
 //     with coalesced loads, score them in float64 exactly as Node.get_value does, and reduce to the FIRST
 //     maximum with shuffles (np.argmax semantics).  Lane 0 then pops the last unexpanded action and creates
 //     the child.
-//   * the rule code of an expansion (make-move, legal moves, transposition key, Game.get_result) is per-THREAD code,
-//     as in k_movegen.  k_select_expand and k_reply therefore work in two phases inside a block of TREE_GAMES games:
-//     phase 1, one warp per game / row -- the cooperative child scans (select) or the legal-masked policy gather and
-//     its first-maximum reduction (reply); __syncthreads(); phase 2, the block's games packed ONE THREAD EACH into the
-//     first warp for the rule code.  (With lane 0 of every warp doing it, 31 of 32 lanes idled through ~3,000
-//     instructions per game: 4,096 games cost 12 M warp instructions instead of 0.4 M.)
+//   * expansion (SelfPlayTree.expand, mctree.py:231-257) stays with the game's warp: the legal moves of the new
+//     position come from the WARP-COOPERATIVE generator (warp_gen.cuh: every lane owns two squares, a packed prefix sum
+//     orders the list as python-chess does), make-move / transposition key / Game.get_result are computed redundantly
+//     by all lanes (uniform, no divergence), lane 0 writes the node.  Measured alternatives, both slower at 4,096
+//     games: lane 0 running the scalar generator (31 lanes idle through ~3,000 dependent instructions, 26 + 34 us for
+//     select / reply) and packing 8 games' scalar generators into one warp (divergence between the 8 boards: 35 + 44 us).
 // With one in-flight simulation per game (the reference's deterministic threads=1 schedule) no atomics are
 // needed on the statistics; the only atomics are the batch-compaction counters.
 #include "engine.cuh"
+#include "warp_gen.cuh"
 
 #include <math_constants.h>
 
 namespace crl {
 
 static constexpr int TREE_BLOCK = 128;
-static constexpr int TREE_GAMES = 8;                    // games (or batch rows) per block of the two-phase kernels
-static constexpr int TREE_THREADS = TREE_GAMES * 32;
+static constexpr int TREE_WARPS = TREE_BLOCK / 32;
 
 __device__ __forceinline__ bool game_running(const Pools& P, int g) {
   return P.g_active[g] && P.g_result[g] == RESULT_NONE;
@@ -61,39 +61,144 @@ struct WarpScan {
   }
 };
 
-__global__ void __launch_bounds__(TREE_THREADS) k_select_expand(Pools P) {
-  __shared__ int s_todo[TREE_GAMES];                    // node to expand per game of the block, -1 = nothing to expand
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  {
-    // phase 1: SelfPlayTree.select's descent (mctree.py:216-225), one warp per game
-    const int g = blockIdx.x * TREE_GAMES + w;
-    int todo = -1;
-    if (g < P.G) {
-      if (!game_running(P, g)) {
-        if (lane == 0) P.s_kind[g] = KIND_IDLE;
-      } else {
-        int node, term;
-        select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
-        if (term) {
-          if (lane == 0) {
-            P.s_node[g] = node;
-            P.s_kind[g] = KIND_TERMINAL;
-          }
-        } else {
-          todo = node;
-        }
-      }
-    }
-    if (lane == 0) s_todo[w] = todo;
+// analyse_position (tree_core.cuh) with the warp-cooperative generator: every lane calls it with the same arguments
+// and gets the same results; the legal moves land in `moves` (shared or global memory).
+__device__ __forceinline__ int analyse_position_warp(const Pools& P, int g, const Board& b, Cursor at, u16* moves, int lane,
+                                                     int* n_moves, u64* key) {
+  int in_check, ep_legal;
+  const int n = warp_generate_legal(b, moves, lane, &in_check, &ep_legal);
+  *n_moves = n;
+  *key = position_key(b, ep_legal);
+  int reps = 0;
+  const int rev = meta_revlen(b.meta);
+  if (rev >= 8 && n > 0 && meta_halfmove(b.meta) < 100 && !insufficient_material(b))
+    reps = count_repetitions(P, g, at, *key, rev);
+  return game_result(b, n, in_check, reps);
+}
+
+// expand_child (tree_core.cuh; mctree.py:241-244) run by the whole warp: uniform reads and arithmetic in every lane,
+// the node's fields written by lane 0, the legal moves of P1 generated cooperatively into the slot's move row.
+__device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot, int parent, int lane, int* out_child) {
+  NodeRec& pn = P.nodes[(long long)g * P.NN + parent];
+  const int child = P.g_nnodes[g];
+  const int k = pn.n_exp;
+  const long long ebase = (long long)g * P.EA + pn.edge0;
+  const u16 mv = P.e_move[ebase + (pn.n_legal - 1 - k)];       // unexpanded_actions.pop(): last legal move first
+  Board b = load_rec(pn.p2);
+  __syncwarp();                                                // every lane has read what lane 0 is about to change
+  if (child >= P.NN) {
+    if (lane == 0) *P.err |= ERR_NODE_OVERFLOW;
+    *out_child = parent;
+    return KIND_IDLE;
   }
-  __syncthreads();
-  // phase 2: SelfPlayTree.expand's first half (mctree.py:241-244), one thread per game
-  if (threadIdx.x >= TREE_GAMES) return;
-  const int g = blockIdx.x * TREE_GAMES + threadIdx.x;
-  const int node = s_todo[threadIdx.x];
-  if (g >= P.G || node < 0) return;
+  make_move(b, mv);
+  NodeRec& cn = P.nodes[(long long)g * P.NN + child];
+  if (lane == 0) {
+    P.g_nnodes[g] = child + 1;
+    store_rec(cn.p1, b);
+    cn.parent = parent;
+    cn.slot = (u8)k;
+    cn.has_p1 = 1;
+    cn.move = mv;
+    cn.reply = MOVE_NONE;
+    cn.n_exp = 0;
+    cn.n_legal = 0;
+    cn.edge0 = 0;
+    cn.pending = 0;
+    P.e_child[ebase + k] = child;
+    P.e_visits[ebase + k] = 0;
+    P.e_value[ebase + k] = 0.0;
+    P.e_vloss[ebase + k] = 0;
+    pn.n_exp = (u16)(k + 1);
+  }
+  __syncwarp();                                                // the repetition walk reads cn.parent in every lane
+  const Cursor at{child, 1, meta_ply(b.meta)};
+  int n_moves;
+  u64 key;
+  const int res = analyse_position_warp(P, g, b, at, P.s_moves + (long long)slot * MAX_MOVES, lane, &n_moves, &key);
+  *out_child = child;
+  if (lane == 0) {
+    cn.key1 = key;
+    P.s_nmoves[slot] = n_moves;
+    if (res != RESULT_NONE) {          // the game ended on our move: the child's state is P1 (mctree.py:244)
+      store_rec(cn.p2, b);
+      cn.key2 = key;
+      cn.result = (int8_t)res;
+      cn.n_legal = (u16)n_moves;
+    } else {
+      cn.result = RESULT_NONE;
+      cn.pending = 1;                  // until the reply is known; only wave-mode selects can meet it
+    }
+    P.e_result[ebase + k] = (int8_t)res;
+  }
+  return res != RESULT_NONE ? KIND_NEW_TERMINAL : KIND_NEED_REPLY;
+}
+
+// reply_child (tree_core.cuh; mctree.py:245-249) run by the whole warp; `gen` = this warp's shared-memory move row
+__device__ __forceinline__ int reply_child_warp(const Pools& P, int g, int slot, int child, int pick, int lane, u16* gen) {
+  NodeRec& cn = P.nodes[(long long)g * P.NN + child];
+  const u16 reply = P.s_moves[(long long)slot * MAX_MOVES + pick];
+  Board b = load_rec(cn.p1);
+  const int parent = cn.parent, cslot = cn.slot;
+  make_move(b, reply);
+  const Cursor at{child, 2, meta_ply(b.meta)};
+  int n2;
+  u64 key;
+  if (lane == 0) cn.reply = reply;     // the walk from P2 steps to P1 of this node only if it has a reply
+  __syncwarp();
+  const int res = analyse_position_warp(P, g, b, at, gen, lane, &n2, &key);
+  const NodeRec& pn = P.nodes[(long long)g * P.NN + parent];
+  const long long pedge = (long long)g * P.EA + pn.edge0 + cslot;
+  int e0 = 0;
+  if (lane == 0) {
+    store_rec(cn.p2, b);
+    cn.key2 = key;
+    cn.result = (int8_t)res;
+    cn.n_legal = (u16)n2;
+    cn.pending = 0;
+    P.e_result[pedge] = (int8_t)res;
+    // reserve the node's edge slots (Node.unexpanded_actions, mctree.py:31); atomic because in wave mode several
+    // rows of one game run concurrently -- where a node's edges sit inside the arena influences no result
+    if (res == RESULT_NONE) e0 = atomicAdd(&P.g_nedges[g], n2);
+  }
+  if (res != RESULT_NONE) return KIND_NEW_TERMINAL;
+  e0 = __shfl_sync(0xffffffffu, e0, 0);
+  if (e0 + n2 > P.EA) {
+    if (lane == 0) {
+      *P.err |= ERR_EDGE_OVERFLOW;
+      cn.n_legal = 0;
+      cn.result = 0;                   // poison as a drawn leaf so the search stays well-defined; the host raises on err
+      P.e_result[pedge] = 0;
+    }
+    return KIND_NEW_TERMINAL;
+  }
+  if (lane == 0) cn.edge0 = e0;
+  __syncwarp();                        // the generated list in shared memory is complete
+  const long long ebase = (long long)g * P.EA + e0;
+  for (int i = lane; i < n2; i += 32) P.e_move[ebase + i] = gen[i];
+  return KIND_EVAL_LEAF;
+}
+
+__global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= P.G) return;
+  if (!game_running(P, g)) {
+    if (lane == 0) P.s_kind[g] = KIND_IDLE;
+    return;
+  }
+  int node, term;
+  select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
+  if (term) {
+    if (lane == 0) {
+      P.s_node[g] = node;
+      P.s_kind[g] = KIND_TERMINAL;
+    }
+    return;
+  }
   int child;
-  int kind = expand_child(P, g, g, node, &child);
+  const int kind = expand_child_warp(P, g, g, node, lane, &child);
+  if (lane != 0) return;
   P.s_node[g] = child;
   P.s_kind[g] = kind;
   if (kind == KIND_NEED_REPLY) {
@@ -126,9 +231,15 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_wave(Pools P) {
     int node = 0;
     const int what = select_descend_wave(P, g, WarpScan<true>{P, g, lane}, &node);
     if (what == 2) break;
+    const int slot = g * P.K + used;
+    // wave_take_slot (tree_core.cuh) with the expansion done by the whole warp
+    int kind = KIND_TERMINAL, leaf = node;
+    if (what != 1) kind = expand_child_warp(P, g, slot, node, lane, &leaf);
     if (lane == 0) {
-      const int slot = g * P.K + used;
-      if (wave_take_slot(P, g, slot, what, node) == KIND_NEED_REPLY) {
+      P.s_node[slot] = leaf;
+      P.s_kind[slot] = kind;
+      if (kind != KIND_IDLE) vloss_add(P, g, leaf, 1);
+      if (kind == KIND_NEED_REPLY) {
         const int row = atomicAdd(P.eval_n, 1);
         P.eval_list[row] = slot;
         P.s_row[slot] = row;
@@ -191,51 +302,44 @@ __global__ void __launch_bounds__(256) k_wave_left(Pools P, int* out) {
 }
 
 // rows of batch A (positions after our move) -> opponent reply, node state, batch B.
-// Phase 1, one WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
-// (agentdistributed.py:56-58).  Phase 2, one THREAD per row: play the reply and build the node (mctree.py:245-249).
-__global__ void __launch_bounds__(TREE_THREADS) k_reply(Pools P, const float* __restrict__ policy,
-                                                        const int16_t* __restrict__ label_of, int* list_b,
-                                                        int* n_b) {
-  __shared__ int s_pick[TREE_GAMES];
-  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// One WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
+// (agentdistributed.py:56-58), then play the reply and build the node together (mctree.py:245-249).
+__global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __restrict__ policy,
+                                                      const int16_t* __restrict__ label_of, int* list_b,
+                                                      int* n_b) {
+  __shared__ u16 s_gen[TREE_WARPS][MAX_MOVES];
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   const int n_a = *P.eval_n;
-  if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
-  {
-    const int r = blockIdx.x * TREE_GAMES + w;
-    if (r < n_a) {
-      const int slot = P.eval_list[r];
-      const float* row = policy + (long long)r * CRL_N_LABELS;
-      const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
-      const int n1 = P.s_nmoves[slot];
-      float best_p = -CUDART_INF_F;
-      int best_i = 0x7fffffff;
-      for (int i = lane; i < n1; i += 32) {
-        const u16 m = moves1[i];
-        const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
-        if (p > best_p) {
-          best_p = p;
-          best_i = i;
-        }
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float op = __shfl_xor_sync(0xffffffffu, best_p, off);
-        const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-        if (op > best_p || (op == best_p && oi < best_i)) {
-          best_p = op;
-          best_i = oi;
-        }
-      }
-      if (lane == 0) s_pick[w] = best_i;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x >= TREE_GAMES) return;
-  const int r = blockIdx.x * TREE_GAMES + threadIdx.x;
+  if (r == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n_a);
   if (r >= n_a) return;
   const int slot = P.eval_list[r];
   const int g = slot / P.K;
-  int kind = reply_child(P, g, slot, P.s_node[slot], policy + (long long)r * CRL_N_LABELS, label_of, s_pick[threadIdx.x]);
+  const int child = P.s_node[slot];
+  const float* row = policy + (long long)r * CRL_N_LABELS;
+  const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
+  const int n1 = P.s_nmoves[slot];
+  float best_p = -CUDART_INF_F;
+  int best_i = 0x7fffffff;
+  for (int i = lane; i < n1; i += 32) {
+    const u16 m = moves1[i];
+    const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    if (p > best_p) {
+      best_p = p;
+      best_i = i;
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float op = __shfl_xor_sync(0xffffffffu, best_p, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+    if (op > best_p || (op == best_p && oi < best_i)) {
+      best_p = op;
+      best_i = oi;
+    }
+  }
+  const int kind = reply_child_warp(P, g, slot, child, best_i, lane, s_gen[threadIdx.x >> 5]);
+  if (lane != 0) return;
   P.s_kind[slot] = kind;
   if (kind == KIND_EVAL_LEAF) {
     int rb = atomicAdd(n_b, 1);
@@ -471,15 +575,15 @@ static int one_simulation(crl_engine_impl* e) {
   e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
-    k_select_expand<<<div_up(e->G, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P);
+    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
     CRL_CUDA(cudaGetLastError());
   }
   int rc = launch_eval_batch(e, 1);
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up(e->G, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, e->d_list[1],
-                                                                      e->d_n + 1);
+    k_reply<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                                   e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);
@@ -509,8 +613,8 @@ static int one_wave(crl_engine_impl* e, int K) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up(e->cur_rows, TREE_GAMES), TREE_THREADS, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
-                                                                             e->d_list[1], e->d_n + 1);
+    k_reply<<<div_up((long long)e->cur_rows * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+                                                                                         e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);

@@ -77,6 +77,15 @@ class Engine:
         check(self.lib.crl_movegen(self.h, _ptr(boards_t), n, _ptr(moves), _ptr(counts), _ptr(flags)))
         return moves, counts, flags
 
+    def movegen_warp(self, boards_t):
+        """Test hook: movegen() through the warp-cooperative generator (crl_debug_movegen_warp)."""
+        n = boards_t.shape[1]
+        moves = torch.empty((n, B.MAX_MOVES), dtype=torch.int16, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        flags = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        check(self.lib.crl_debug_movegen_warp(self.h, _ptr(boards_t), n, _ptr(moves), _ptr(counts), _ptr(flags)))
+        return moves, counts, flags
+
     def make_moves(self, boards_t, moves_t):
         check(self.lib.crl_make_moves(self.h, _ptr(boards_t), boards_t.shape[1], _ptr(moves_t)))
         return boards_t

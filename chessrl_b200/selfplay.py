@@ -242,8 +242,13 @@ def main(argv=None):
     if rank == 0:
         data.save(os.path.join(args.model_dir, "gameplays.json"))
         if not args.no_train:
-            logger.info("Training on %d game(s)" % len(data))
-            agent.train(data, logdir=args.model_dir, epochs=1, validation_split=0, batch_size=1)
+            # The reference trains after EVERY game in a fresh process -- Agent(True, model_path), i.e. a new Adam state,
+            # one epoch over that one game (selfplay.py:98-108, 155-162) -- while its PredictWorker keeps the starting
+            # weights for the whole run (reload_model is never called).  Playing all games first with the starting
+            # weights and then training game by game, each with a fresh optimizer, gives the same sequence of updates.
+            for i, g in enumerate(data.games):
+                logger.info("\tTraining %d of %d" % (i + 1, len(data)))
+                agent.train(DatasetGame([g]), logdir=args.model_dir, epochs=1, validation_split=0, batch_size=1)
             agent.save(model_path)
 
 

@@ -77,6 +77,10 @@ int crl_version(void);
  * moves_dev [n][CRL_MAX_MOVES], counts_dev [n], flags_dev [n] (bit0 in check, bit1 legal ep exists; may be NULL) */
 int crl_movegen(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* moves_dev, int32_t* counts_dev,
                 uint8_t* flags_dev);
+/* test hook: the same lists from the WARP-COOPERATIVE generator (32 lanes on one board; csrc/warp_gen.cuh) that the tree
+ * kernels and the small breadth-first perft plies use where boards are few and latency is everything */
+int crl_debug_movegen_warp(crl_engine* e, const uint64_t* boards_dev, int n, uint16_t* moves_dev, int32_t* counts_dev,
+                           uint8_t* flags_dev);
 /* Board.push behind Game.move (game.py:28-41), no legality check; in place. moves_dev [n]; 0xFFFF = skip */
 int crl_make_moves(crl_engine* e, uint64_t* boards_dev, int n, const uint16_t* moves_dev);
 /* perft: each lane walks its own subtree depth-first; bulk != 0 counts the last ply without making moves */

@@ -14,11 +14,12 @@ from collections import defaultdict
 
 rep, kre, cubin, kname = sys.argv[1:5]
 top = int(sys.argv[5]) if len(sys.argv) > 5 else 40
+COL = sys.argv[6] if len(sys.argv) > 6 else "Instructions Executed"     # e.g. "# Samples" = where the TIME goes
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre, "--launch-count", "1"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
-ci, cs = hdr.index("Instructions Executed"), hdr.index("Source")
+ci, cs = hdr.index(COL), hdr.index("Source")
 sass = []
 for r in rows[2:]:
     if r and r[0] == "Kernel Name":          # the page repeats per captured launch: keep the first
@@ -44,7 +45,7 @@ agg = defaultdict(int)
 for loc, (_, n) in zip(lines, sass):
     agg[loc] += n
 tot = sum(agg.values())
-print("total warp instructions executed: %d over %d SASS instructions" % (tot, len(sass)))
+print("total %s: %d over %d SASS instructions" % (COL, tot, len(sass)))
 src = {}
 for (f, l), n in sorted(agg.items(), key=lambda kv: -kv[1])[:top]:
     if f not in src:

@@ -8,7 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_hostsim.so")
 _SRC = os.path.join(_HERE, "hostsim.cpp")
 _CSRC = os.path.join(_HERE, "..", "..", "chessrl_b200", "csrc")
-_DEPS = [os.path.join(_CSRC, f) for f in ("chess_core.cuh", "tree_core.cuh", "hash_eval.cuh")]
+_DEPS = [os.path.join(_CSRC, f) for f in ("chess_core.cuh", "tree_core.cuh", "hash_eval.cuh", "warp_gen.cuh")]
 
 
 def load():
@@ -19,6 +19,8 @@ def load():
     u64p = ctypes.POINTER(ctypes.c_uint64)
     lib.hs_movegen.argtypes = [u64p, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_int)]
     lib.hs_movegen.restype = ctypes.c_int
+    lib.hs_movegen_warp.argtypes = [u64p, ctypes.POINTER(ctypes.c_uint16), ctypes.POINTER(ctypes.c_int)]
+    lib.hs_movegen_warp.restype = ctypes.c_int
     lib.hs_make.argtypes = [u64p, ctypes.c_uint16]
     lib.hs_make.restype = None
     lib.hs_key.argtypes = [u64p, ctypes.c_int]

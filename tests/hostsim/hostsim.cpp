@@ -2,6 +2,7 @@
 // It exists so the rule kernels' arithmetic can be checked against the oracle in the CPU-only build
 // container.  It is NOT part of libchessrl_b200.so and nothing under chessrl_b200/ loads it.
 #include "../../chessrl_b200/csrc/chess_core.cuh"
+#include "../../chessrl_b200/csrc/warp_gen.cuh"
 #include <string.h>
 using namespace crl;
 
@@ -19,6 +20,36 @@ int hs_movegen(const uint64_t* rec, uint16_t* out, int* flags) {
   flags[0] = gi.in_check;
   flags[1] = gi.ep_legal;
   return s.n;
+}
+
+// the warp-cooperative generator (warp_gen.cuh) with its 32 lanes run one after the other and the shuffle prefix sum
+// done in a loop: same per-lane code as the device, so its move lists can be checked against the scalar generator here
+int hs_movegen_warp(const uint64_t* rec, uint16_t* out, int* flags) {
+  Board b;
+  memcpy(b.bb, rec, 64);
+  b.meta = rec[8];
+  WgCommon c;
+  wg_common(b, c);
+  flags[0] = c.in_check;
+  flags[1] = 0;
+  if (!c.valid) return 0;
+  WgLane w[32];
+  uint64_t incl[32], run = 0;
+  for (int lane = 0; lane < 32; ++lane) {
+    wg_lane(b, c, lane, w[lane]);
+    run += w[lane].packed;
+    incl[lane] = run;
+  }
+  for (int i = 0; i < MAX_MOVES; ++i) out[i] = 0xEEEE;
+  WgOffsets r0;
+  for (int lane = 0; lane < 32; ++lane) {
+    WgOffsets r;
+    wg_offsets(incl[lane], w[lane].packed, run, c.in_check ? popc64(c.king_moves) : 0, c.n_castle, r);
+    wg_emit(c, lane, w[lane], r, out);
+    if (lane == 0) r0 = r;
+  }
+  int n_ep = wg_emit_rest(b, c, r0, out, &flags[1]);
+  return r0.base6 + n_ep;
 }
 
 void hs_make(uint64_t* rec, uint16_t mv) {

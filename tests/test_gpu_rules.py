@@ -270,6 +270,24 @@ def test_rules_on_unreachable_random_positions(engine1):
     assert k == kids.shape[1]
 
 
+def test_warp_cooperative_generator_equals_k_movegen(engine1):
+    """crl_debug_movegen_warp (warp_gen.cuh, the generator behind the tree expansions and the small perft plies) against
+    k_movegen, list for list in order, with the in-check / legal-ep flags: 6,000 fuzzed positions, 40,000 of their
+    children, the perft suite and the 218-move positions."""
+    rng = random.Random(5)
+    fens = [position_fuzz.random_fen(rng)[0] for _ in range(6000)] + [f for f, _ in perft_kats.EDGE] + perft_kats.MAX_MOVES
+    recs = np.stack([B.record_from_fen(f) for f in fens])
+    t = engine1.boards_to_device(recs)
+    kids, _ = engine1.expand_frontier(t[:, :1500].contiguous())
+    t = torch.cat([t, kids[:, :40000]], dim=1).contiguous()
+    mv, cn, fl = engine1.movegen(t)
+    mw, cw, fw = engine1.movegen_warp(t)
+    assert torch.equal(cn, cw) and torch.equal(fl, fw)
+    idx = torch.arange(B.MAX_MOVES, device=mv.device)[None, :] < cn[:, None]
+    assert torch.equal(torch.where(idx, mv, torch.zeros_like(mv)), torch.where(idx, mw, torch.zeros_like(mw)))
+    assert int(cn.max()) == 218 and int((fl & 1).sum()) > 1000 and int((fl & 2).sum()) > 100
+
+
 def test_movegen_order_invariants_on_device(engine1):
     """k_movegen's lists against the structural order rules of python-chess (tests/move_order_rules.py: class order
     1-6, from / to descending, q r b n, king evasions first) -- a validator that generates no move itself -- over

@@ -370,3 +370,59 @@ def test_device_history_walk_matches_planes(lib):
                             got[r, f, 14 * s + ci + 1 + pt] = 1
         got[:, :, 126] = 1.0 if child.state.turn else 0.0
         assert (got == planes).all(), k
+
+
+def movegen_warp(lib, rec):
+    out = (ctypes.c_uint16 * 256)()
+    fl = (ctypes.c_int * 2)()
+    n = lib.hs_movegen_warp(rec.ctypes.data_as(u64p), out, fl)
+    return [int(out[i]) for i in range(n)], fl[0], fl[1], [int(out[i]) for i in range(n, 256)]
+
+
+def movegen_words(lib, rec):
+    out = (ctypes.c_uint16 * 256)()
+    fl = (ctypes.c_int * 2)()
+    n = lib.hs_movegen(rec.ctypes.data_as(u64p), out, fl)
+    return [int(out[i]) for i in range(n)], fl[0], fl[1]
+
+
+def test_warp_cooperative_generator_equals_scalar_generator(lib):
+    """warp_gen.cuh (32 lanes on one board: per-lane squares + packed prefix sum) run lane by lane on the host:
+    the same list in the same ORDER as generate_legal, the same flags, nothing written past the end -- over 6,000
+    fuzzed positions (promoted material, checks, double checks, pins, castling, en passant), their children, the perft
+    suite, the two 218-move positions and a 300-ply game."""
+    import random
+    rng = random.Random(31)
+    recs = [B.record_from_fen(f) for f, _ in PERFT] + [B.record_from_fen(f) for f in perft_kats.MAX_MOVES] + \
+           [B.record_from_fen(f) for f, _ in perft_kats.EDGE]
+    seen = {"check": 0, "double": 0, "castle": 0, "promo": 0, "ep": 0, "pinned": 0}
+    for _ in range(6000):
+        fen, b = position_fuzz.random_fen(rng)
+        recs.append(B.record_from_fen(fen))
+        if bin(b.checkers_mask()).count("1") > 1:
+            seen["double"] += 1
+    b = chess.Board()
+    for _ in range(300):
+        ms = list(b.legal_moves)
+        if not ms:
+            break
+        b.push(rng.choice(ms))
+        recs.append(B.record_from_fen(b.fen()))
+    extra = []
+    for rec in recs[:600]:                                   # one ply deeper: positions after every legal move
+        words, _, _ = movegen_words(lib, rec)
+        for w in words[:6]:
+            child = rec.copy()
+            lib.hs_make(child.ctypes.data_as(u64p), w)
+            extra.append(child)
+    for rec in recs + extra:
+        want, chk, epl = movegen_words(lib, rec)
+        got, chk2, epl2, tail = movegen_warp(lib, rec)
+        assert got == want, B.fen_from_record(rec)
+        assert (chk, epl) == (chk2, epl2)
+        assert all(x == 0xEEEE for x in tail)                 # no stray writes beyond the list
+        seen["check"] += chk
+        seen["ep"] += epl
+        seen["promo"] += any(w >> 12 for w in want)
+        seen["castle"] += any((w & 63) in (4, 60) and abs(((w >> 6) & 63) - (w & 63)) == 2 for w in want)
+    assert seen["check"] > 1000 and seen["double"] > 20 and seen["castle"] > 300 and seen["promo"] > 500 and seen["ep"] > 200, seen
