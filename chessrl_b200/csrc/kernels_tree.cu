@@ -61,6 +61,30 @@ struct WarpScan {
   }
 };
 
+// count_repetitions (tree_core.cuh) by the whole warp: the walk through the tree's own positions is a pointer chase and
+// stays serial (a handful of steps, the same in every lane); once it reaches the game's key ring the remaining positions
+// have known addresses, so the lanes compare them in parallel -- up to 127 dependent loads become four.
+__device__ __forceinline__ int count_repetitions_warp(const Pools& P, int g, Cursor c, u64 key, int revlen, int lane) {
+  if (revlen > KEY_RING - 1) revlen = KEY_RING - 1;
+  int reps = 0, i = 0;
+  while (i < revlen && c.node >= 0) {
+    if (!cursor_prev(P, g, c)) return reps;
+    ++i;
+    if (c.node >= 0 && cursor_key(P, g, c) == key) ++reps;
+  }
+  if (c.node >= 0) return reps;                    // the reversible run ended inside the tree
+  // c now points at the ring position of ply c.ply, reached by step i but not compared yet; the serial walk would
+  // compare it and then step (revlen - i) more times, never below ply 0
+  int m = revlen - i + 1;
+  if (m > c.ply + 1) m = c.ply + 1;
+  int mine = 0;
+  for (int j = lane; j < m; j += 32)
+    mine += P.g_keys[(long long)((c.ply - j) % KEY_RING) * P.G + g] == key;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  return reps + mine;
+}
+
 // analyse_position (tree_core.cuh) with the warp-cooperative generator: every lane calls it with the same arguments
 // and gets the same results; the legal moves land in `moves` (shared or global memory).
 __device__ __forceinline__ int analyse_position_warp(const Pools& P, int g, const Board& b, Cursor at, u16* moves, int lane,
@@ -72,7 +96,7 @@ __device__ __forceinline__ int analyse_position_warp(const Pools& P, int g, cons
   int reps = 0;
   const int rev = meta_revlen(b.meta);
   if (rev >= 8 && n > 0 && meta_halfmove(b.meta) < 100 && !insufficient_material(b))
-    reps = count_repetitions(P, g, at, *key, rev);
+    reps = count_repetitions_warp(P, g, at, *key, rev, lane);
   return game_result(b, n, in_check, reps);
 }
 

@@ -346,3 +346,53 @@ def test_batched_lane_calls_match_the_per_lane_ones():
     rec, _, _ = e.games_get(0, 6)
     assert (rec[1] == B.record_from_fen()).all() and (rec[4] == B.record_from_fen()).all()
     e.close()
+
+
+def test_pool_overflow_is_reported_once_and_does_not_poison_the_engine():
+    """A node / edge pool overflow sets a device flag that every *_host call checks; it must be reported (CRL_ENOMEM)
+    and then CLEARED, so that a later search on the same engine -- other games, or the same lanes reloaded -- works."""
+    from chessrl_b200._lib import CRL_ENOMEM, EVAL_HASH, CrlError
+    from chessrl_b200.engine import Engine
+    e = Engine(max_games=2, max_nodes=60, avg_moves=1)          # 512 edge slots per game: ~20 nodes' worth
+    e.set_evaluator(EVAL_HASH, 3, 24)
+    start = np.tile(B.record_from_fen(), (2, 1))
+    e.games_set(start)
+    e.mcts_begin_move()
+    e.mcts_simulate(60)
+    with pytest.raises(CrlError) as err:
+        e.root_stats()
+    assert err.value.status == CRL_ENOMEM
+    e.games_set(start)                                          # reload the lanes; the flag was cleared by the report
+    e.mcts_begin_move()
+    e.mcts_simulate(10)
+    st = e.root_stats()
+    assert (st["root_visits"] == 11).all() and (st["visits"].sum(1) == 10).all()
+    e.close()
+
+
+def test_search_move_picks_before_building_views_and_views_are_lazy(golden_dir):
+    """SelfPlayTree.search_move commits the pick before any Node view replays a position on the shared one-lane engine
+    (ADVICE r1): the returned pair equals the golden, the views still expose the reference's attributes, and touching
+    them afterwards does not disturb a second search."""
+    from chessrl_b200 import mctree
+    from chessrl_b200.agentdistributed import AgentDistributed
+    from chessrl_b200.game import Game
+    cases = json.load(open(os.path.join(golden_dir, "mcts_chess.json")))["cases"]
+    case = next(c for c in cases if c["name"] == "random12_47" and c["sims"] == 30 and c["policy_bits"] == 24)
+    g = Game()
+    for m in case["moves"]:
+        assert g.move(m)
+    agent = AgentDistributed(True)
+    agent.use_hash_evaluator(case["eval_seed"], case["policy_bits"])
+    tree = mctree.SelfPlayTree(g, threads=1)
+    ret = tree.search_move(agent, max_iters=case["sims"], noise=False, ai_move=True)
+    assert list(ret) == case["returned"]
+    kids = tree.root.children
+    assert [c.visits for c in kids] == [k["visits"] for k in case["children"]]
+    assert all(c._state is None for c in kids)                               # nothing replayed yet
+    n_root = len(g.board.move_stack)
+    assert [[str(m) for m in c.state.board.move_stack][n_root:] for c in kids] == [k["line"] for k in case["children"]]
+    assert [float(c.get_value()).hex() for c in kids] == [k["score"] for k in case["children"]]
+    assert [len(c.children) for c in kids] == [k["n_children"] for k in case["children"]]
+    tree2 = mctree.SelfPlayTree(g, threads=1)                                # the views' replays left no trace
+    assert list(tree2.search_move(agent, max_iters=case["sims"], noise=False, ai_move=True)) == case["returned"]
