@@ -205,44 +205,38 @@ def perft_metric(engine):
 
 
 def perft_sharded(engine, rank, world, dist):
-    """perft over all ranks: the breadth-first frontier (>= 65,536 boards) is sharded board i -> rank i % world, every
-    rank walks its share, ONE all_reduce(sum) of a uint64 per root joins the counts.  Deeper roots
-    than the single-GPU variant so that every rank has work: start depth 6 / 7, Kiwipete depth 5 / 6."""
+    """perft over all ranks, ONE crl_perft_root_shard_host call per rank and root: every rank expands the first plies on
+    its own GPU (device-side, no host round trip); once a frontier holds >= 65,536 boards each rank keeps its contiguous
+    share, expands it further on its own and walks it; ONE all_reduce(sum) of an int64 per root joins the counts
+    (SURVEY.md 8(e)).  The timed region is the whole call -- root in, shard total out -- max over ranks."""
     import torch
     from chessrl_b200 import boards as B
     from chessrl_b200 import sharding
     out = {}
     for name, fen, depth, want in (("start_d6", B.STARTING_FEN, 6, 119060324), ("kiwipete_d5", KIWI, 5, 193690690),
                                    ("start_d7", B.STARTING_FEN, 7, 3195901860), ("kiwipete_d6", KIWI, 6, 8031647685)):
-        best, best_walk = None, None
-        for rep in range(4):
+        rec = B.record_from_fen(fen)
+        min_frontier = max(1 << 16, ((1 << 20) if depth <= 5 else (1 << 26)) // world)
+        best, lanes = None, 0
+        for rep in range(4):                                   # the first call sizes the frontier buffers
             dist.barrier()
             torch.cuda.synchronize()
-            a, m, b = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            # every rank expands the (small) upper plies itself -- cheaper than scattering boards -- then takes its share
-            frontier = engine.boards_to_device(B.record_from_fen(fen)[None, :])
-            d = 0
-            while frontier.shape[1] < (65536 if depth <= 5 else (1 << 20)) and d < depth - 1:
-                frontier, _ = engine.expand_frontier(frontier)
-                d += 1
-            mine = frontier[:, rank::world].contiguous()
-            m.record()
-            nodes = engine.perft(mine, depth - d, bulk=True)
+            mine, lanes, plies = engine.perft_root(rec, depth, bulk=True, min_frontier=min_frontier, shard=rank,
+                                                   n_shards=world, shard_min_frontier=1 << 16)
             b.record()
             torch.cuda.synchronize()
-            t = torch.tensor([a.elapsed_time(b), m.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total = sharding.sum_counts(nodes)                             # one all_reduce(sum) of an int64
+            total = sharding.sum_counts([mine])                            # one all_reduce(sum) of an int64
             assert total == want, (name, total, want)
             if rep > 0:
-                best = float(t[0].item()) if best is None else min(best, float(t[0].item()))
-                best_walk = float(t[1].item()) if best_walk is None else min(best_walk, float(t[1].item()))
+                best = float(t.item()) if best is None else min(best, float(t.item()))
         out[name] = {"nodes": want, "ms_max_over_ranks": best, "nodes_per_s": want / best * 1e3,
-                     "timed": "frontier expansion (replicated on every rank, host-driven plies) + this rank's walk",
-                     "ms_walk_only_max_over_ranks": best_walk, "nodes_per_s_walk_only": want / best_walk * 1e3,
-                     "frontier_boards": int(frontier.shape[1]), "boards_per_rank": int(mine.shape[1]),
-                     "leaf_bulk_counting": True}
+                     "timed": "the whole sharded call on every rank: replicated first plies, own share from a >= 65,536-board "
+                              "frontier on, walk; max over ranks",
+                     "lanes_this_rank": int(lanes), "breadth_first_plies": int(plies), "leaf_bulk_counting": True}
     return out
 
 

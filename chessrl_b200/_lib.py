@@ -48,6 +48,8 @@ SIGNATURES = {
     "crl_make_moves": (ctypes.c_int, [vp, vp, ctypes.c_int, vp]),
     "crl_perft": (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]),
     "crl_perft_root_host": (ctypes.c_int, [vp, c_u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_u64p, c_i64p, c_i32p]),
+    "crl_perft_root_shard_host": (ctypes.c_int, [vp, c_u64p, ctypes.c_int, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_int64, c_u64p, c_i64p, c_i32p]),
     "crl_expand_frontier": (ctypes.c_int, [vp, vp, ctypes.c_int, vp, vp, ctypes.c_int64, vp]),
     "crl_game_replay_host": (ctypes.c_int, [vp, c_u64p, c_u16p, ctypes.c_int, c_u16p, c_i32p, c_i8p, c_u8p, c_u64p]),
     "crl_game_replay_records_host": (ctypes.c_int, [vp, c_u64p, c_u16p, ctypes.c_int, c_u16p, c_i32p, c_i8p, c_u8p,

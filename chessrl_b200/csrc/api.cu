@@ -376,18 +376,27 @@ int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int b
 }
 int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier,
                         uint64_t* total_host, int64_t* lanes_host, int32_t* bfs_plies_host) {
+  return crl_perft_root_shard_host(e, root_host, depth, bulk, min_frontier, 0, 1, 1, total_host, lanes_host, bfs_plies_host);
+}
+
+int crl_perft_root_shard_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier, int shard,
+                              int n_shards, int64_t shard_min_frontier, uint64_t* total_host, int64_t* lanes_host,
+                              int32_t* bfs_plies_host) {
   CHECK_ENGINE(e);
-  if (!root_host || !total_host || depth < 0 || min_frontier < 1) {
+  if (!root_host || !total_host || depth < 0 || min_frontier < 1 || n_shards < 1 || shard < 0 || shard >= n_shards ||
+      shard_min_frontier < 1) {
     set_error("crl_perft_root_host: bad arguments");
     return CRL_EINVAL;
   }
   if (!e->perft_ctl) {
-    CRL_CUDA(cudaMalloc((void**)&e->perft_ctl, 8 * sizeof(unsigned long long)));
+    CRL_CUDA(cudaMalloc((void**)&e->perft_ctl, 16 * sizeof(unsigned long long)));
     e->allocs.push_back(e->perft_ctl);
   }
   // capacity: the frontier stops growing once it holds min_frontier boards, so 16x leaves room for one more ply of a
   // quiet position; a bushier frontier overflows, which is detected on the device and retried with four times the room
+  // (a sharded call keeps the replicated frontier below 218 x shard_min boards before it is split)
   long long cap = min_frontier * 16;
+  if (n_shards > 1 && shard_min_frontier * 256 > cap) cap = shard_min_frontier * 256;
   if (cap < (1 << 16)) cap = 1 << 16;
   const long long cap_max = 320LL << 20;       // 320 Mi boards = 23 GB per buffer: holds Kiwipete's depth-5 frontier
   if (cap > cap_max) cap = min_frontier * 2 > cap_max ? min_frontier * 2 : cap_max;
@@ -410,14 +419,14 @@ int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int
     const long long stride = e->perft_cap;
     // the root record travels as a kernel parameter (no copy), the control block is initialised on the device
     int rc = launch_perft_root(e, root_host, e->perft_buf[0], e->perft_buf[1], stride, e->perft_ctl, depth, bulk,
-                               min_frontier, e->perft_pair);
+                               min_frontier, e->perft_pair, shard, n_shards, shard_min_frontier);
     if (rc) return rc;
     if ((rc = ensure_stage(e, 64))) return rc;
     unsigned long long* ctl = (unsigned long long*)e->h_stage;          // pinned: the read-back is one async copy
     CRL_CUDA(cudaMemcpyAsync(ctl, e->perft_ctl, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     CRL_CUDA(cudaStreamSynchronize(e->stream));
     if (ctl[3] == 0) {
-      *total_host = depth == 0 ? 1 : ctl[4];
+      *total_host = depth == 0 ? (shard == 0 ? 1 : 0) : ctl[4];
       // boards the walk ran on in lockstep: the stored frontier, or -- when the last two plies went through
       // k_perft_pair -- the boards of the last-but-one ply it dealt to its lanes (ctl[5]; never stored)
       if (lanes_host) *lanes_host = (int64_t)(ctl[5] ? ctl[5] : ctl[0]);

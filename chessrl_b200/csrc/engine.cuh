@@ -118,7 +118,7 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
 int launch_frontier(crl_engine_impl* e, const u64* boards, int n, const long long* offsets, u64* out,
                     long long out_n, int* counts);
 int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl,
-                      int depth, int bulk, long long min_frontier, int pair);
+                      int depth, int bulk, long long min_frontier, int pair, int shard, int n_shards, long long shard_min);
 int launch_encode_boards(crl_engine_impl* e, const u64* boards, const u64* hist, const u8* hist_len, int n,
                          __nv_bfloat16* planes);
 int launch_policy_index(crl_engine_impl* e, const u16* moves, const int* counts, int n, int16_t* idx);

@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ b
 // sequence blindly: no count pass, no prefix sum, no synchronisation between plies.
 //   ctl[0] boards in the current frontier   ctl[1] boards placed so far in the next one (atomic)
 //   ctl[2] plies expanded                   ctl[3] overflow flag (next frontier > capacity)     ctl[4] total (atomic)
+//   ctl[5] boards dealt by k_perft_pair     ctl[6] blocks of the running ply that have finished
+//   ctl[8] index of the current frontier's first board inside its buffer                       ctl[9] "sharded" flag
+// SHARDING over ranks (crl_perft_root_shard_host): every rank expands the same first plies; as soon as a committed frontier
+// holds >= shard_min boards, each rank keeps only its contiguous share [n*s/S, n*(s+1)/S) of it (ctl[8], ctl[0]) and goes
+// on alone -- no board ever crosses a link, one all_reduce(sum) of the per-rank totals joins the counts.
 // Frontiers ping-pong between buf[0] and buf[1] (SoA with stride `cap`); the current one is buf[ctl[2] & 1].
 // does the next ply still expand breadth-first?  Yes while the frontier is small, or while the remaining depth is
 // more than one lane's stack can walk; never beyond depth-1 plies (the last ply is always counted by the walk).
@@ -199,6 +204,12 @@ __device__ __forceinline__ bool bfs_active(CtlPtr ctl, long long min_frontier, i
 // lane makes one move per step and the 72-byte records of 32 consecutive children are stored with nine fully coalesced
 // 256-byte writes (one lane writing all children of its own parent scatters 8-byte stores over 32 different rows).
 static constexpr int BFS_CAP = 96;          // moves per parent staged in shared memory; the (rare) rest stays with its lane
+
+struct ShardSpec {
+  int shard, n_shards;
+  long long shard_min;
+};
+static constexpr int CTL_WORDS = 16;
 
 struct BfsSink {
   static constexpr bool kCounting = false;
@@ -328,23 +339,33 @@ __device__ __forceinline__ void bfs_expand_warp(const u64* __restrict__ in, u64*
 static constexpr long long BFS_WARP_MAX = 12288;   // frontiers up to this size expand one warp per parent
 
 // the frontier just written becomes the current one
-__device__ __forceinline__ void bfs_commit(unsigned long long* ctl) {
+__device__ __forceinline__ void bfs_take_shard(unsigned long long* ctl, const ShardSpec& sh) {
+  const unsigned long long n = ctl[0];
+  const unsigned long long lo = n * (unsigned long long)sh.shard / (unsigned long long)sh.n_shards;
+  const unsigned long long hi = n * (unsigned long long)(sh.shard + 1) / (unsigned long long)sh.n_shards;
+  ctl[8] += lo;
+  ctl[0] = hi - lo;
+  ctl[9] = 1;
+}
+__device__ __forceinline__ void bfs_commit(unsigned long long* ctl, const ShardSpec& sh) {
   ctl[0] = ctl[1];
   ctl[1] = 0;
   ctl[2] += 1;
+  ctl[8] = 0;                                                           // a new frontier starts at the buffer's first board
+  if (sh.n_shards > 1 && !ctl[9] && (long long)ctl[0] >= sh.shard_min) bfs_take_shard(ctl, sh);
 }
 
 // One grid-wide ply.  The LAST block to finish commits the ply (ctl[6] counts finished blocks), so a ply is one launch.
 __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0, u64* __restrict__ buf1, long long cap,
                                                          unsigned long long* __restrict__ ctl, long long min_frontier,
-                                                         int depth, int pair) {
+                                                         int depth, int pair, ShardSpec sh) {
   __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
   __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
   __shared__ int s_pre[RULES_BLOCK / 32][33];
   if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid: nobody commits before
   const long long n = (long long)ctl[0];                              // every block has read the control block
   const int plies = (int)ctl[2];
-  const u64* in = (plies & 1) ? buf1 : buf0;
+  const u64* in = ((plies & 1) ? buf1 : buf0) + ctl[8];
   u64* out = (plies & 1) ? buf0 : buf1;
   if (n <= BFS_WARP_MAX)
     bfs_expand_warp(in, out, cap, n, ctl, (long long)blockIdx.x * (RULES_BLOCK / 32) + (threadIdx.x >> 5),
@@ -357,7 +378,7 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0,
     __threadfence();
     if (atomicAdd(&ctl[6], 1ull) + 1 == (unsigned long long)gridDim.x) {
       ctl[6] = 0;
-      bfs_commit(ctl);
+      bfs_commit(ctl, sh);
     }
   }
 }
@@ -372,9 +393,10 @@ static constexpr int FIRST_THREADS = 512;          // 16 warps: the 20 children 
 static constexpr long long FIRST_MAX = 96;         // k_bfs_first keeps going while the frontier is at most this large
 __global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u64* __restrict__ buf0, u64* __restrict__ buf1,
                                                              long long cap, unsigned long long* __restrict__ ctl,
-                                                             long long min_frontier, int depth, int pair, int n_plies) {
+                                                             long long min_frontier, int depth, int pair, int n_plies,
+                                                             ShardSpec sh) {
   __shared__ u16 s_gen[FIRST_THREADS / 32][MAX_MOVES];
-  if (threadIdx.x < 8) ctl[threadIdx.x] = threadIdx.x == 0 ? 1ull : 0ull;
+  if (threadIdx.x < CTL_WORDS) ctl[threadIdx.x] = threadIdx.x == 0 ? 1ull : 0ull;
   if (threadIdx.x < 9) buf0[(long long)threadIdx.x * cap] = root.w[threadIdx.x];     // column 0 of the SoA buffer
   __syncthreads();
   const volatile unsigned long long* vctl = ctl;
@@ -383,22 +405,28 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u6
     const long long n = (long long)vctl[0];
     if (n > FIRST_MAX) break;                                          // the grid-wide ply kernels take over
     const int plies = (int)vctl[2];
-    const u64* in = (plies & 1) ? buf1 : buf0;
+    const u64* in = ((plies & 1) ? buf1 : buf0) + vctl[8];
     u64* out = (plies & 1) ? buf0 : buf1;
     __syncthreads();
     bfs_expand_warp(in, out, cap, n, ctl, threadIdx.x >> 5, FIRST_THREADS / 32, s_gen[threadIdx.x >> 5]);
     __syncthreads();
-    if (threadIdx.x == 0) bfs_commit(ctl);
+    if (threadIdx.x == 0) bfs_commit(ctl, sh);
     __syncthreads();
   }
 }
 __global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
                                                             long long cap, unsigned long long* __restrict__ ctl, int depth,
-                                                            int bulk, int pair) {
+                                                            int bulk, int pair, ShardSpec sh) {
   if (ctl[3]) return;
-  const long long n = (long long)ctl[0];
+  long long n = (long long)ctl[0];
+  long long first = (long long)ctl[8];
+  if (sh.n_shards > 1 && !ctl[9]) {      // the frontier never grew to shard_min boards: the ranks split it here
+    const long long lo = n * sh.shard / sh.n_shards, hi = n * (sh.shard + 1) / sh.n_shards;
+    first += lo;
+    n = hi - lo;
+  }
   const int plies = (int)ctl[2];
-  const u64* in = (plies & 1) ? buf1 : buf0;
+  const u64* in = ((plies & 1) ? buf1 : buf0) + first;
   const int remaining = depth - plies;
   if (pair && remaining == 2) return;                                  // k_perft_pair counts these
   unsigned long long mine = 0;
@@ -452,7 +480,7 @@ __global__ void __launch_bounds__(RULES_BLOCK, MINB) k_perft_pair(const u64* __r
   const long long n = (long long)ctl[0];
   const int plies = (int)ctl[2];
   if (depth - plies != 2) return;                                      // uniform for the whole grid
-  const u64* in = (plies & 1) ? buf1 : buf0;
+  const u64* in = ((plies & 1) ? buf1 : buf0) + ctl[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_warps = (long long)gridDim.x * (RULES_BLOCK / 32);
   // boards per warp and round: 32 when that still leaves >= 32 warp-rounds per SM, else fewer (phase 1 then runs on
@@ -584,7 +612,9 @@ int launch_perft(crl_engine_impl* e, const u64* boards, int n, int depth, int bu
 }
 // enqueues the whole device-driven perft of `root` (AoS record, host): the first kernel stores it and initialises ctl
 int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1, long long cap, unsigned long long* ctl,
-                      int depth, int bulk, long long min_frontier, int pair) {
+                      int depth, int bulk, long long min_frontier, int pair, int shard, int n_shards, long long shard_min) {
+  const ShardSpec sh{shard, n_shards, shard_min};
+  if (n_shards > 1) pair = 0;            // the optional two-ply pass is a single-GPU experiment
   if (depth < 0 || depth > 64) {
     set_error("crl_perft_root_host: depth %d is not supported", depth);
     return CRL_EINVAL;
@@ -599,7 +629,7 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
   for (int k = 0; k < 9; ++k) rr.w[k] = root[k];
   {
     LaunchScope ls(e, KC_MOVEGEN);
-    k_bfs_first<<<1, FIRST_THREADS, 0, e->stream>>>(rr, buf0, buf1, cap, ctl, min_frontier, depth, pair, first_plies);
+    k_bfs_first<<<1, FIRST_THREADS, 0, e->stream>>>(rr, buf0, buf1, cap, ctl, min_frontier, depth, pair, first_plies, sh);
     CRL_CUDA(cudaGetLastError());
   }
   // How many boards a ply holds is only known on the device (and whether the first kernel ran one ply or two), so
@@ -608,7 +638,7 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
   for (int ply = 1; ply < max_plies; ++ply) {
     {
       LaunchScope ls(e, KC_MOVEGEN);
-      k_bfs_ply<<<max_grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair);
+      k_bfs_ply<<<max_grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair, sh);
       CRL_CUDA(cudaGetLastError());
     }
     bound = bound * 218 < cap ? bound * 218 : cap;
@@ -627,7 +657,7 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
       else k_perft_pair<0, 6><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
     }
   }
-  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk, pair);
+  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk, pair, sh);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

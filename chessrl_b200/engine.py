@@ -96,15 +96,18 @@ class Engine:
         check(self.lib.crl_perft(self.h, _ptr(boards_t), n, int(depth), int(bool(bulk)), _ptr(nodes)))
         return nodes
 
-    def perft_root(self, record, depth, bulk=True, min_frontier=1 << 20):
+    def perft_root(self, record, depth, bulk=True, min_frontier=1 << 20, shard=0, n_shards=1, shard_min_frontier=1 << 16):
         """perft(depth) of one position in ONE call: device-side breadth-first plies to >= min_frontier boards, then a
-        depth-first walk per lane.  Returns (total, lanes, bfs_plies)."""
+        depth-first walk per lane.  Returns (total, lanes, bfs_plies).  With n_shards > 1 the call computes shard
+        `shard`'s part only (the frontier is split once it holds >= shard_min_frontier boards); the shards' totals add up
+        to perft(depth)."""
         rec = np.ascontiguousarray(np.asarray(record, dtype=np.uint64).reshape(9))
         total = ctypes.c_uint64(0)
         lanes = ctypes.c_int64(0)
         plies = ctypes.c_int32(0)
-        check(self.lib.crl_perft_root_host(self.h, _np(rec, ctypes.c_uint64), int(depth), int(bool(bulk)), int(min_frontier),
-                                           ctypes.byref(total), ctypes.byref(lanes), ctypes.byref(plies)))
+        check(self.lib.crl_perft_root_shard_host(self.h, _np(rec, ctypes.c_uint64), int(depth), int(bool(bulk)),
+                                                 int(min_frontier), int(shard), int(n_shards), int(shard_min_frontier),
+                                                 ctypes.byref(total), ctypes.byref(lanes), ctypes.byref(plies)))
         return int(total.value), int(lanes.value), int(plies.value)
 
     def expand_frontier(self, boards_t):

@@ -270,6 +270,20 @@ def test_rules_on_unreachable_random_positions(engine1):
     assert k == kids.shape[1]
 
 
+@pytest.mark.parametrize("fen,depth,want", [(B.STARTING_FEN, 5, 4865609), (KIWI, 4, 4085603), (KIWI, 5, 193690690),
+                                            ("8/2p5/3p4/KP5r/1R3p1k/8/4P1P1/8 w - - 0 1", 6, 11030083)])
+def test_perft_root_sharded_totals_add_up(engine1, fen, depth, want):
+    """crl_perft_root_shard_host: the shards' totals add up to the published perft, wherever the split happens (in a
+    breadth-first ply, or only at the walk because the frontier never reached shard_min) and however the lanes divide."""
+    rec = B.record_from_fen(fen)
+    for n_shards, shard_min, min_frontier in ((2, 1 << 16, 1 << 18), (3, 200, 5000), (8, 1 << 12, 1 << 16), (5, 1 << 40, 1 << 12)):
+        parts = [engine1.perft_root(rec, depth, bulk=(s % 2 == 0), min_frontier=min_frontier, shard=s, n_shards=n_shards,
+                                    shard_min_frontier=shard_min) for s in range(n_shards)]
+        assert sum(p[0] for p in parts) == want, (n_shards, shard_min, [p[0] for p in parts])
+        assert all(p[0] > 0 for p in parts)
+    assert engine1.perft_root(rec, depth)[0] == want                      # the unsharded call is shard 0 of 1
+
+
 def test_warp_cooperative_generator_equals_k_movegen(engine1):
     """crl_debug_movegen_warp (warp_gen.cuh, the generator behind the tree expansions and the small perft plies) against
     k_movegen, list for list in order, with the in-check / legal-ep flags: 6,000 fuzzed positions, 40,000 of their
