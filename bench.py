@@ -206,9 +206,9 @@ def perft_metric(engine):
 
 def perft_sharded(engine, rank, world, dist):
     """perft over all ranks, ONE crl_perft_root_shard_host call per rank and root: every rank expands the first plies on
-    its own GPU (device-side, no host round trip); once a frontier holds >= 65,536 boards each rank keeps its contiguous
-    share, expands it further on its own and walks it; ONE all_reduce(sum) of an int64 per root joins the counts
-    (SURVEY.md 8(e)).  The timed region is the whole call -- root in, shard total out -- max over ranks."""
+    its own GPU (device-side, no host round trip); the first ply whose input frontier holds >= 4,096 boards keeps only
+    the children that hash to this rank, which then expands and walks its own boards alone; ONE all_reduce(sum) of an int64
+    per root joins the counts.  The timed region is the whole call -- root in, shard total out -- max over ranks."""
     import torch
     from chessrl_b200 import boards as B
     from chessrl_b200 import sharding
@@ -224,7 +224,7 @@ def perft_sharded(engine, rank, world, dist):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             mine, lanes, plies = engine.perft_root(rec, depth, bulk=True, min_frontier=min_frontier, shard=rank,
-                                                   n_shards=world, shard_min_frontier=1 << 16)
+                                                   n_shards=world, shard_min_frontier=1 << 12)
             b.record()
             torch.cuda.synchronize()
             t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
@@ -234,8 +234,8 @@ def perft_sharded(engine, rank, world, dist):
             if rep > 0:
                 best = float(t.item()) if best is None else min(best, float(t.item()))
         out[name] = {"nodes": want, "ms_max_over_ranks": best, "nodes_per_s": want / best * 1e3,
-                     "timed": "the whole sharded call on every rank: replicated first plies, own share from a >= 65,536-board "
-                              "frontier on, walk; max over ranks",
+                     "timed": "the whole sharded call on every rank: replicated first plies, own boards (by record hash) from the "
+                              "first >= 4,096-board frontier on, walk; max over ranks",
                      "lanes_this_rank": int(lanes), "breadth_first_plies": int(plies), "leaf_bulk_counting": True}
     return out
 

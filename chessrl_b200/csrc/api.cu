@@ -383,8 +383,8 @@ int crl_perft_root_shard_host(crl_engine* e, const uint64_t* root_host, int dept
                               int n_shards, int64_t shard_min_frontier, uint64_t* total_host, int64_t* lanes_host,
                               int32_t* bfs_plies_host) {
   CHECK_ENGINE(e);
-  if (!root_host || !total_host || depth < 0 || min_frontier < 1 || n_shards < 1 || shard < 0 || shard >= n_shards ||
-      shard_min_frontier < 1) {
+  if (shard_min_frontier < 128) shard_min_frontier = 128;     // the first kernel's tiny plies are never split
+  if (!root_host || !total_host || depth < 0 || min_frontier < 1 || n_shards < 1 || shard < 0 || shard >= n_shards) {
     set_error("crl_perft_root_host: bad arguments");
     return CRL_EINVAL;
   }
@@ -394,9 +394,9 @@ int crl_perft_root_shard_host(crl_engine* e, const uint64_t* root_host, int dept
   }
   // capacity: the frontier stops growing once it holds min_frontier boards, so 16x leaves room for one more ply of a
   // quiet position; a bushier frontier overflows, which is detected on the device and retried with four times the room
-  // (a sharded call keeps the replicated frontier below 218 x shard_min boards before it is split)
+  // (a sharded call replicates frontiers below shard_min boards, so the first filtered one is below 218 x shard_min / n)
   long long cap = min_frontier * 16;
-  if (n_shards > 1 && shard_min_frontier * 256 > cap) cap = shard_min_frontier * 256;
+  if (n_shards > 1 && shard_min_frontier * 64 > cap) cap = shard_min_frontier * 64;
   if (cap < (1 << 16)) cap = 1 << 16;
   const long long cap_max = 320LL << 20;       // 320 Mi boards = 23 GB per buffer: holds Kiwipete's depth-5 frontier
   if (cap > cap_max) cap = min_frontier * 2 > cap_max ? min_frontier * 2 : cap_max;

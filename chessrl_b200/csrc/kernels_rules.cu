@@ -181,10 +181,12 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft(const u64* __restrict__ b
 //   ctl[0] boards in the current frontier   ctl[1] boards placed so far in the next one (atomic)
 //   ctl[2] plies expanded                   ctl[3] overflow flag (next frontier > capacity)     ctl[4] total (atomic)
 //   ctl[5] boards dealt by k_perft_pair     ctl[6] blocks of the running ply that have finished
-//   ctl[8] index of the current frontier's first board inside its buffer                       ctl[9] "sharded" flag
-// SHARDING over ranks (crl_perft_root_shard_host): every rank expands the same first plies; as soon as a committed frontier
-// holds >= shard_min boards, each rank keeps only its contiguous share [n*s/S, n*(s+1)/S) of it (ctl[8], ctl[0]) and goes
-// on alone -- no board ever crosses a link, one all_reduce(sum) of the per-rank totals joins the counts.
+//   ctl[9] "sharded" flag
+// SHARDING over ranks (crl_perft_root_shard_host): every rank expands the same first plies; the first ply whose INPUT
+// frontier holds >= shard_min boards stores only the children that belong to this rank -- shard_of(board) == shard, a hash
+// of the child's record, because the atomic placement orders the frontier differently on every rank and in every call, so
+// an index range would not partition it -- and from then on each rank expands and walks its own boards alone.  No board
+// ever crosses a link; one all_reduce(sum) of the per-rank totals joins the counts.
 // Frontiers ping-pong between buf[0] and buf[1] (SoA with stride `cap`); the current one is buf[ctl[2] & 1].
 // does the next ply still expand breadth-first?  Yes while the frontier is small, or while the remaining depth is
 // more than one lane's stack can walk; never beyond depth-1 plies (the last ply is always counted by the walk).
@@ -210,6 +212,12 @@ struct ShardSpec {
   long long shard_min;
 };
 static constexpr int CTL_WORDS = 16;
+// which rank a board belongs to: any function of the record alone will do (transpositions land on the same rank)
+__device__ __forceinline__ int shard_of(const Board& b, int n_shards) {
+  const u64 x = (b.bb[OCC_W] * 0x9E3779B97F4A7C15ULL) ^ (b.bb[OCC_B] * 0xC2B2AE3D27D4EB4FULL) ^ b.bb[PAWN] ^ (b.bb[QUEEN] << 1) ^
+                (b.bb[ROOK] >> 1) ^ b.meta;
+  return (int)(mix64(x) % (u64)n_shards);
+}
 
 struct BfsSink {
   static constexpr bool kCounting = false;
@@ -242,9 +250,12 @@ typedef u16 (*BfsMoves)[32][BFS_CAP];
 typedef int (*BfsPre)[33];
 
 // one breadth-first ply over parents i0, i0 + istride, ... of `in` (n boards) for the calling thread's warp
+// FILTER: the ply that splits the frontier over the ranks keeps only this rank's children (compacted per round of 32
+// with a ballot, one atomicAdd per round)
+template <bool FILTER>
 __device__ __forceinline__ void bfs_expand(const u64* __restrict__ in, u64* __restrict__ out, long long cap, long long n,
                                            unsigned long long* __restrict__ ctl, long long i0, long long istride,
-                                           BfsBoards s_board, BfsMoves s_moves, BfsPre s_pre) {
+                                           BfsBoards s_board, BfsMoves s_moves, BfsPre s_pre, int shard, int n_shards) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_pad = (n + 31) & ~31LL;                            // whole warps stay together
   for (long long i = i0; i < n_pad; i += istride) {
@@ -269,31 +280,51 @@ __device__ __forceinline__ void bfs_expand(const u64* __restrict__ in, u64* __re
     s_pre[warp][lane] = pre - sink.n;
     if (lane == 31) s_pre[warp][32] = warp_total;
     unsigned long long base = 0;
-    if (lane == 0 && warp_total) base = atomicAdd(&ctl[1], (unsigned long long)warp_total);
-    base = __shfl_sync(0xffffffffu, base, 0);
+    if (!FILTER) {
+      if (lane == 0 && warp_total) base = atomicAdd(&ctl[1], (unsigned long long)warp_total);
+      base = __shfl_sync(0xffffffffu, base, 0);
+    }
     __syncwarp();
-    if (base + warp_total > (unsigned long long)cap) {
+    if (!FILTER && base + warp_total > (unsigned long long)cap) {
       if (lane == 0) ctl[3] = 1;
       __syncwarp();
       continue;
     }
     // ---- phase 2: children dealt round-robin ----
-    for (int j = lane; j < warp_total; j += 32) {
-      int lo = 0, hi = 32;
-#pragma unroll
-      for (int step = 0; step < 5; ++step) {
-        const int mid = (lo + hi) >> 1;
-        if (s_pre[warp][mid] <= j) lo = mid;
-        else hi = mid;
-      }
-      const int k = j - s_pre[warp][lo];
-      if (k >= BFS_CAP) continue;                                      // stays with its parent's lane (phase 3)
+    for (int j0 = 0; j0 < warp_total; j0 += 32) {
+      const int j = j0 + lane;
+      bool keep = false;
       Board c;
+      if (j < warp_total) {
+        int lo = 0, hi = 32;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) c.bb[w] = s_board[warp][w][lo];
-      c.meta = s_board[warp][8][lo];
-      make_move(c, s_moves[warp][lo][k]);
-      store_soa(out, cap, (long long)base + j, c);
+        for (int step = 0; step < 5; ++step) {
+          const int mid = (lo + hi) >> 1;
+          if (s_pre[warp][mid] <= j) lo = mid;
+          else hi = mid;
+        }
+        const int k = j - s_pre[warp][lo];
+        if (k < BFS_CAP) {                                             // else: stays with its parent's lane (phase 3)
+#pragma unroll
+          for (int w = 0; w < 8; ++w) c.bb[w] = s_board[warp][w][lo];
+          c.meta = s_board[warp][8][lo];
+          make_move(c, s_moves[warp][lo][k]);
+          keep = !FILTER || shard_of(c, n_shards) == shard;
+        }
+      }
+      if (!FILTER) {
+        if (keep) store_soa(out, cap, (long long)base + j, c);
+      } else {
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        unsigned long long rbase = 0;
+        if (lane == 0 && mask) rbase = atomicAdd(&ctl[1], (unsigned long long)__popc(mask));
+        rbase = __shfl_sync(0xffffffffu, rbase, 0);
+        if (rbase + __popc(mask) > (unsigned long long)cap) {
+          if (lane == 0) ctl[3] = 1;
+        } else if (keep) {
+          store_soa(out, cap, (long long)rbase + __popc(mask & ((1u << lane) - 1)), c);
+        }
+      }
     }
     // ---- phase 3: parents with more than BFS_CAP moves finish their own list ----
     if (sink.n > BFS_CAP) {
@@ -301,7 +332,13 @@ __device__ __forceinline__ void bfs_expand(const u64* __restrict__ in, u64* __re
       for (int k = BFS_CAP; k < sink.n; ++k) {
         Board c = b;
         make_move(c, spill[k - BFS_CAP]);
-        store_soa(out, cap, o + k, c);
+        if (!FILTER) {
+          store_soa(out, cap, o + k, c);
+        } else if (shard_of(c, n_shards) == shard) {
+          const unsigned long long at = atomicAdd(&ctl[1], 1ull);
+          if (at + 1 > (unsigned long long)cap) ctl[3] = 1;
+          else store_soa(out, cap, (long long)at, c);
+        }
       }
     }
     __syncwarp();                                                      // the rows are reused by the next round
@@ -338,21 +375,18 @@ __device__ __forceinline__ void bfs_expand_warp(const u64* __restrict__ in, u64*
 }
 static constexpr long long BFS_WARP_MAX = 12288;   // frontiers up to this size expand one warp per parent
 
-// the frontier just written becomes the current one
-__device__ __forceinline__ void bfs_take_shard(unsigned long long* ctl, const ShardSpec& sh) {
-  const unsigned long long n = ctl[0];
-  const unsigned long long lo = n * (unsigned long long)sh.shard / (unsigned long long)sh.n_shards;
-  const unsigned long long hi = n * (unsigned long long)(sh.shard + 1) / (unsigned long long)sh.n_shards;
-  ctl[8] += lo;
-  ctl[0] = hi - lo;
-  ctl[9] = 1;
+// does the ply that expands the current frontier split it over the ranks?  (uniform: read before anybody commits)
+template <class CtlPtr>
+__device__ __forceinline__ bool bfs_splits(CtlPtr ctl, const ShardSpec& sh) {
+  return sh.n_shards > 1 && !ctl[9] && (long long)ctl[0] >= sh.shard_min;
 }
+// the frontier just written becomes the current one
 __device__ __forceinline__ void bfs_commit(unsigned long long* ctl, const ShardSpec& sh) {
+  const bool split = bfs_splits(ctl, sh);
   ctl[0] = ctl[1];
   ctl[1] = 0;
   ctl[2] += 1;
-  ctl[8] = 0;                                                           // a new frontier starts at the buffer's first board
-  if (sh.n_shards > 1 && !ctl[9] && (long long)ctl[0] >= sh.shard_min) bfs_take_shard(ctl, sh);
+  if (split) ctl[9] = 1;
 }
 
 // One grid-wide ply.  The LAST block to finish commits the ply (ctl[6] counts finished blocks), so a ply is one launch.
@@ -365,14 +399,16 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0,
   if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid: nobody commits before
   const long long n = (long long)ctl[0];                              // every block has read the control block
   const int plies = (int)ctl[2];
-  const u64* in = ((plies & 1) ? buf1 : buf0) + ctl[8];
+  const u64* in = (plies & 1) ? buf1 : buf0;
   u64* out = (plies & 1) ? buf0 : buf1;
-  if (n <= BFS_WARP_MAX)
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, tstride = (long long)gridDim.x * blockDim.x;
+  if (bfs_splits(ctl, sh))
+    bfs_expand<true>(in, out, cap, n, ctl, t0, tstride, s_board, s_moves, s_pre, sh.shard, sh.n_shards);
+  else if (n <= BFS_WARP_MAX)
     bfs_expand_warp(in, out, cap, n, ctl, (long long)blockIdx.x * (RULES_BLOCK / 32) + (threadIdx.x >> 5),
                     (long long)gridDim.x * (RULES_BLOCK / 32), &s_moves[threadIdx.x >> 5][0][0]);
   else
-    bfs_expand(in, out, cap, n, ctl, (long long)blockIdx.x * blockDim.x + threadIdx.x, (long long)gridDim.x * blockDim.x,
-               s_board, s_moves, s_pre);
+    bfs_expand<false>(in, out, cap, n, ctl, t0, tstride, s_board, s_moves, s_pre, 0, 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
@@ -405,7 +441,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u6
     const long long n = (long long)vctl[0];
     if (n > FIRST_MAX) break;                                          // the grid-wide ply kernels take over
     const int plies = (int)vctl[2];
-    const u64* in = ((plies & 1) ? buf1 : buf0) + vctl[8];
+    const u64* in = (plies & 1) ? buf1 : buf0;
     u64* out = (plies & 1) ? buf0 : buf1;
     __syncthreads();
     bfs_expand_warp(in, out, cap, n, ctl, threadIdx.x >> 5, FIRST_THREADS / 32, s_gen[threadIdx.x >> 5]);
@@ -418,20 +454,18 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restric
                                                             long long cap, unsigned long long* __restrict__ ctl, int depth,
                                                             int bulk, int pair, ShardSpec sh) {
   if (ctl[3]) return;
-  long long n = (long long)ctl[0];
-  long long first = (long long)ctl[8];
-  if (sh.n_shards > 1 && !ctl[9]) {      // the frontier never grew to shard_min boards: the ranks split it here
-    const long long lo = n * sh.shard / sh.n_shards, hi = n * (sh.shard + 1) / sh.n_shards;
-    first += lo;
-    n = hi - lo;
-  }
+  const long long n = (long long)ctl[0];
+  const bool split_here = sh.n_shards > 1 && !ctl[9];     // the frontier never grew to shard_min boards: split it now
   const int plies = (int)ctl[2];
-  const u64* in = ((plies & 1) ? buf1 : buf0) + first;
+  const u64* in = (plies & 1) ? buf1 : buf0;
   const int remaining = depth - plies;
   if (pair && remaining == 2) return;                                  // k_perft_pair counts these
   unsigned long long mine = 0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    mine += remaining <= 0 ? 1ull : perft_lane(load_soa(in, cap, i), remaining, bulk);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const Board b = load_soa(in, cap, i);
+    if (split_here && shard_of(b, sh.n_shards) != sh.shard) continue;
+    mine += remaining <= 0 ? 1ull : perft_lane(b, remaining, bulk);
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&ctl[4], mine);
@@ -480,7 +514,7 @@ __global__ void __launch_bounds__(RULES_BLOCK, MINB) k_perft_pair(const u64* __r
   const long long n = (long long)ctl[0];
   const int plies = (int)ctl[2];
   if (depth - plies != 2) return;                                      // uniform for the whole grid
-  const u64* in = ((plies & 1) ? buf1 : buf0) + ctl[8];
+  const u64* in = (plies & 1) ? buf1 : buf0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long n_warps = (long long)gridDim.x * (RULES_BLOCK / 32);
   // boards per warp and round: 32 when that still leaves >= 32 warp-rounds per SM, else fewer (phase 1 then runs on

@@ -97,9 +97,11 @@ int crl_perft(crl_engine* e, const uint64_t* boards_dev, int n, int depth, int b
 int crl_perft_root_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier,
                         uint64_t* total_host, int64_t* lanes_host, int32_t* bfs_plies_host);
 /* the same perft SHARDED over n_shards callers (one per GPU): every caller expands the same first plies on its own device;
- * as soon as a frontier holds >= shard_min_frontier boards, caller `shard` keeps only its contiguous share of it and goes
- * on alone (further plies until its own frontier holds >= min_frontier boards, then the walk).  *total_host = THIS
- * shard's count; the sum over the shards is perft(depth) (one all_reduce(sum)).  No board crosses a link. */
+ * the first ply whose input frontier holds >= shard_min_frontier boards keeps only the children whose record hashes to
+ * `shard` (the atomic placement orders a frontier differently in every call, so an index range would not partition it),
+ * and the caller goes on alone (further plies until its own frontier holds >= min_frontier boards, then the walk).
+ * *total_host = THIS shard's count; the sum over the shards is perft(depth) (one all_reduce(sum)).  No board
+ * crosses a link. */
 int crl_perft_root_shard_host(crl_engine* e, const uint64_t* root_host, int depth, int bulk, int64_t min_frontier, int shard,
                               int n_shards, int64_t shard_min_frontier, uint64_t* total_host, int64_t* lanes_host,
                               int32_t* bfs_plies_host);
