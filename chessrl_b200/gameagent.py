@@ -12,33 +12,38 @@ from .agent import Agent
 from .game import Game
 
 
+def _as_agent(agent, player_color):
+    if isinstance(agent, Agent):
+        return agent
+    if type(agent) == str:                       # a weights path: the agent takes the colour the player did not
+        return Agent(not player_color, weights=agent)
+    raise ValueError("An agent or path to the agents weights (.h5) is needed")
+
+
 class GameAgent(Game):
 
     def __init__(self, agent, player_color=Game.WHITE, board=None, date=None):
         super().__init__(board=board, player_color=player_color, date=date)
-        if isinstance(agent, Agent):
-            self.agent = agent
-        elif type(agent) == str:
-            self.agent = Agent(not player_color, weights=agent)
-        else:
-            raise ValueError("An agent or path to the agents weights (.h5) is needed")
+        self.agent = _as_agent(agent, player_color)
+
+    def _agent_plays(self):
+        return Game.move(self, self.agent.best_move(self, real_game=True))
 
     def move(self, movement):
-        """Makes a move; the agent replies.  An illegal move is ignored (returns False) (gameagent.py:25-43)."""
-        if self.agent.color and len(self.board.move_stack) == 0:
-            # agent plays white and nothing has been played yet: it opens, `movement` is not played
-            return super().move(self.agent.best_move(self, real_game=True))
-        made_movement = super().move(movement)
-        if made_movement and self.get_result() is None:
-            super().move(self.agent.best_move(self, real_game=True))
-        return made_movement
+        """Plays `movement` and lets the agent reply; an illegal move is ignored and returns False.  On an empty
+        board with the agent as white, the agent opens instead and `movement` is not played (gameagent.py:25-43)."""
+        if self.agent.color and not self.board.move_stack:
+            return self._agent_plays()
+        accepted = Game.move(self, movement)
+        if accepted and self.get_result() is None:
+            self._agent_plays()
+        return accepted
 
     def get_copy(self):
-        g = Game.get_copy(self)
-        g.__class__ = GameAgent
-        g.agent = self.agent
-        g.player_color = self.player_color
-        return g
+        twin = Game.get_copy(self)
+        twin.__class__ = GameAgent
+        twin.agent, twin.player_color = self.agent, self.player_color
+        return twin
 
     def tearup(self):
         """Free resources."""
