@@ -67,6 +67,20 @@ def edge_slots_per_node(lanes, nodes, device=None, bytes_per_edge=24, share=0.5)
     return max(48, min(218, fit))
 
 
+TOWER_ROUND = 592          # positions one round of the persistent tower kernel covers: 74 CTA pairs x 8 boards
+
+
+def default_lanes(n_games):
+    """Lanes for a finite run when --lanes is not given.  Two effects pull in opposite directions: a finished game's lane
+    is refilled only while games are left, so few games per lane means a long drain at low occupancy (one game per lane:
+    ~50 %, four: ~78 %, sixteen: ~94 % -- game lengths have a long tail); and the tower is most efficient on batches that
+    are multiples of one round of its persistent grid.  Rule: about four games per lane, a whole number of tower rounds,
+    at most seven rounds (4,144 lanes, where the step is tensor-bound anyway); small runs take one lane per game."""
+    if n_games <= TOWER_ROUND:
+        return max(1, n_games)
+    return min(7 * TOWER_ROUND, max(TOWER_ROUND, (n_games // 4) // TOWER_ROUND * TOWER_ROUND))
+
+
 class LockstepRun:
     """The many-games form of selfplay.py's game loop (selfplay.py:142-163) on one GPU: `lanes` games advance in
     lockstep, a lane whose game ends is refilled with the next game at once (per-GPU slot refill) and
@@ -206,7 +220,8 @@ def main(argv=None):
                         help="MCTS simulations in flight per game (reference default 6; 1 = its deterministic schedule)")
     parser.add_argument('--debug', action='store_true', default=False, help="Log debug messages on screen. Default false.")
     parser.add_argument('--sims', type=int, default=900, help="MCTS simulations per move (reference: 900)")
-    parser.add_argument('--lanes', type=int, default=None, help="games stepped in lockstep per GPU")
+    parser.add_argument('--lanes', type=int, default=None,
+                        help="games stepped in lockstep per GPU (default: about four games per lane in whole tower rounds)")
     parser.add_argument('--max-moves', type=int, default=None, help="cap on the agent's moves per game (stored unfinished)")
     parser.add_argument('--no-train', action='store_true', default=False)
     args = parser.parse_args(argv)
@@ -229,7 +244,8 @@ def main(argv=None):
     share = args.games // world + (1 if rank < args.games % world else 0)
     logger.info("rank %d/%d plays %d game(s), %d simulations per move" % (rank, world, share, args.sims))
     stats = {}
-    data = (play_games_lockstep(agent.model, share, sims=args.sims, lanes=args.lanes, device=local_rank,
+    lanes = args.lanes if args.lanes is not None else default_lanes(share)
+    data = (play_games_lockstep(agent.model, share, sims=args.sims, lanes=lanes, device=local_rank,
                                 threads=args.threads, max_moves=args.max_moves, stats=stats) if share else DatasetGame())
     if stats:
         full = max(1, stats["steps"] * stats["lanes"] * args.sims)

@@ -113,3 +113,11 @@ def test_keras_checkpoint_layer_mapping_and_hdf5_detection(tmp_path):
             ChessModel(weights=str(fake))
     with pytest.raises(OSError):
         ChessModel(weights=str(tmp_path / "missing.h5"))   # supervised.py:57-59 catches OSError for a missing file
+
+
+def test_default_lane_count_balances_drain_and_tower_rounds():
+    from chessrl_b200.selfplay import TOWER_ROUND, default_lanes
+    assert default_lanes(1) == 1 and default_lanes(500) == 500 and default_lanes(592) == 592
+    assert default_lanes(593) == 592 and default_lanes(4096) == 592           # 1,024 -> one whole round
+    assert default_lanes(8192) == 3 * 592 and default_lanes(65536) == 7 * 592
+    assert all(default_lanes(n) % TOWER_ROUND == 0 for n in range(600, 70000, 997))
