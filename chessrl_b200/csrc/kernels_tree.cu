@@ -203,7 +203,8 @@ __device__ __forceinline__ int reply_child_warp(const Pools& P, int g, int slot,
   return KIND_EVAL_LEAF;
 }
 
-__global__ void __launch_bounds__(TREE_BLOCK) k_select_expand(Pools P) {
+// (7 blocks = 28 warps per SM: 148 x 28 = 4,144 resident warps, so 4,096 games run as ONE wave instead of 1.5)
+__global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= P.G) return;
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(256) k_wave_left(Pools P, int* out) {
 // rows of batch A (positions after our move) -> opponent reply, node state, batch B.
 // One WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
 // (agentdistributed.py:56-58), then play the reply and build the node together (mctree.py:245-249).
-__global__ void __launch_bounds__(TREE_BLOCK) k_reply(Pools P, const float* __restrict__ policy,
+__global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, const float* __restrict__ policy,
                                                       const int16_t* __restrict__ label_of, int* list_b,
                                                       int* n_b) {
   __shared__ u16 s_gen[TREE_WARPS][MAX_MOVES];
