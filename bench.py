@@ -240,8 +240,12 @@ def perft_sharded(engine, rank, world, dist):
     return out
 
 
-def whole_games_steady_state(model_pack, lanes, sims, inflight, n_steps, seed):
-    """The path selfplay.py runs (chessrl_b200.selfplay.LockstepRun: harvest finished games -> refill their lanes ->
+def whole_games_steady_state(model_pack, lanes, sims, inflight, n_steps, seed, reuse=False):
+    """reuse=False: every search evaluates every position (comparable with the per-move `value`); reuse=True: what
+    selfplay.py runs by default -- evaluations of the previous move's search of the same game are looked up instead of
+    run again (crl_set_reuse; same games move for move, tests/test_gpu_reuse.py), so a simulation costs fewer than two
+    network evaluations.
+    The path selfplay.py runs (chessrl_b200.selfplay.LockstepRun: harvest finished games -> refill their lanes ->
     one lockstep move for all lanes incl. the host-side move pick) in its steady state, timed by WALL CLOCK.
     Lanes start at staggered phases (0..300 random plies) so games end -- and lanes are harvested and refilled -- at
     their natural rate inside the timed window; the supply of games is unbounded, so there is no drain tail here
@@ -254,7 +258,7 @@ def whole_games_steady_state(model_pack, lanes, sims, inflight, n_steps, seed):
     eng.load_weights(model_pack)
     eng.set_evaluator(EVAL_NET)
     start, move_lists = synthetic_games(eng, lanes, seed, lo=0, hi=300, start_fraction=0.0)
-    run = LockstepRun(None, None, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, engine=eng)
+    run = LockstepRun(None, None, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, engine=eng, reuse=reuse)
     np.random.seed(seed)
     run.start(start_records=start, move_lists=eng.pack_move_lists(move_lists))
     run.advance()                                                   # warm-up step (graph capture, first refills)
@@ -274,12 +278,14 @@ def whole_games_steady_state(model_pack, lanes, sims, inflight, n_steps, seed):
            "games_finished": run.finished_games - f0, "lanes_refilled": run.refills - r0,
            "games_per_s_at_this_phase_mix": (run.finished_games - f0) / dt,
            "lane_occupancy": sims_done / max(1, n_steps * lanes * sims),
-           "evaluations_per_simulation": (c1["evaluations"] - c0["evaluations"]) / max(1, sims_done)}
+           "evaluations_per_simulation": (c1["evaluations"] - c0["evaluations"]) / max(1, sims_done),
+           "evaluation_reuse": bool(reuse),
+           "reused_evaluations_per_simulation": (c1["reused_evaluations"] - c0["reused_evaluations"]) / max(1, sims_done)}
     eng.close()
     return out
 
 
-def whole_games_complete_run(model_pack, n_games, lanes, sims, inflight, seed):
+def whole_games_complete_run(model_pack, n_games, lanes, sims, inflight, seed, reuse=True):
     """A complete finite self-play run through chessrl_b200.selfplay.play_games_lockstep, drain tail included."""
     from chessrl_b200 import model
     from chessrl_b200.selfplay import play_games_lockstep
@@ -287,7 +293,8 @@ def whole_games_complete_run(model_pack, n_games, lanes, sims, inflight, seed):
     m.weights = model_pack
     np.random.seed(seed)
     stats = {}
-    data = play_games_lockstep(m, n_games, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, stats=stats)
+    data = play_games_lockstep(m, n_games, sims=sims, lanes=lanes, noise=True, seed=seed, threads=inflight, stats=stats,
+                               reuse=reuse)
     res = [g.get_result() for g in data.games]
     stats.update({"games": len(data), "mean_plies": float(np.mean([len(g) for g in data.games])),
                   "white_wins": res.count(1), "black_wins": res.count(-1), "draws": res.count(0), "unfinished": res.count(None),
@@ -751,12 +758,16 @@ def main():
     if rank == 0 and not args.no_kernels:
         kernels = kernel_rooflines(eng, peaks, flush, True)
     whole = None
+    whole_reuse = None
     complete = None
     large = None
     eng.close()                                      # the legs below size their own engines
     if rank == 0 and not args.no_whole_games:
         whole = whole_games_steady_state(pack, args.wg_lanes or G, args.wg_sims or S, K, args.wg_steps, seed=7)
         whole["fraction_of_device_resident_value"] = whole["simulations_per_s"] / (value / world) if (args.wg_lanes or G) == G and (args.wg_sims or S) == S else None
+        if K == 1:      # the same loop with evaluation reuse on (selfplay.py's default): same games, fewer evaluations
+            whole_reuse = whole_games_steady_state(pack, args.wg_lanes or G, args.wg_sims or S, K, args.wg_steps, seed=7, reuse=True)
+            whole_reuse["speedup_over_no_reuse"] = whole_reuse["simulations_per_s"] / whole["simulations_per_s"]
     if rank == 0 and args.whole_games > 0:
         complete = whole_games_complete_run(pack, args.whole_games, args.wg_lanes or G, args.wg_sims or S, K, seed=7)
     if not args.no_large:
@@ -788,7 +799,7 @@ def main():
             "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
             "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
             "roofline": roof, "cpu_baseline": cpu, "perft": perft, "perft_sharded": perft_multi, "kernels": kernels,
-            "whole_games": whole, "whole_games_complete_run": complete, "large_config": large,
+            "whole_games": whole, "whole_games_reuse": whole_reuse, "whole_games_complete_run": complete, "large_config": large,
         }
         print(json.dumps(line))
     if world > 1:

@@ -107,6 +107,7 @@ static int check_pool_errors(crl_engine_impl* e) {
     // report once and clear: kernels only OR into the flag, and one overflowing game must not make every later call
     // on this engine fail (the offending lanes keep whatever partial state they have; callers reload them)
     CRL_CUDA(cudaMemsetAsync(e->P.err, 0, sizeof(int), e->stream));
+    CRL_CUDA(cudaMemsetAsync(e->P.g_prev_root, 0xFF, sizeof(int) * (size_t)e->G, e->stream));   // no reuse of a broken tree
     set_error("pool overflow on the device (flags %d: 1 = nodes per game, 2 = edges per game, 4 = plies per game); "
               "create the engine with larger max_nodes / avg_moves", err);
     return CRL_ENOMEM;
@@ -279,6 +280,7 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   A(e_vloss, G * e->EA);
   A(r_visits, G);
   A(r_value, G);
+  A(g_prev_root, G);
   A(s_node, R);
   A(s_kind, R);
   A(s_moves, R * MAX_MOVES);
@@ -306,6 +308,10 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
                                      cudaMemcpyHostToDevice, e->stream);
     if (ce != cudaSuccess) rc = cuda_fail(ce, "label table upload");
   }
+  if (rc == CRL_OK) {
+    cudaError_t ce = cudaMemsetAsync(P.g_prev_root, 0xFF, sizeof(int) * G, e->stream);
+    if (ce != cudaSuccess) rc = cuda_fail(ce, "g_prev_root init");
+  }
   if (rc == CRL_OK) rc = net_create(e);
   if (rc == CRL_OK) {
     cudaError_t ce = cudaStreamSynchronize(e->stream);
@@ -329,7 +335,8 @@ int crl_destroy(crl_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   drain_profile(e);
-  if (e->sim_graph) cudaGraphExecDestroy(e->sim_graph);
+  for (int i = 0; i < 2; ++i)
+    if (e->sim_graph[i]) cudaGraphExecDestroy(e->sim_graph[i]);
   net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
   if (e->d_stage) cudaFree(e->d_stage);
@@ -801,9 +808,41 @@ int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t
   return check_pool_errors(e);
 }
 
+int crl_set_reuse(crl_engine* e, int enable) {
+  CHECK_ENGINE(e);
+  if (enable && !e->P.nodes_prev) {
+    // the second set of tree pools: node records, and the two edge arrays a twin lookup reads (child index, prior)
+    const size_t G = e->G;
+    int rc = pool_alloc(e, &e->P.nodes_prev, G * e->NN);
+    if (rc == CRL_OK) rc = pool_alloc(e, &e->P.e_prior_prev, G * e->EA);
+    if (rc == CRL_OK) rc = pool_alloc(e, &e->P.e_child_prev, G * e->EA);
+    if (rc != CRL_OK) {
+      e->P.nodes_prev = nullptr;   // (what was allocated stays in e->allocs and is freed with the engine)
+      return rc;
+    }
+  }
+  CRL_CUDA(cudaMemsetAsync(e->P.g_prev_root, 0xFF, sizeof(int) * (size_t)e->G, e->stream));
+  e->reuse = enable != 0;
+  e->tree_ready = false;
+  return CRL_OK;
+}
+
+int crl_reuse_count_host(crl_engine* e, int64_t* reused_host) {
+  CHECK_ENGINE(e);
+  if (!reused_host) {
+    set_error("crl_reuse_count_host: null output");
+    return CRL_EINVAL;
+  }
+  long long c = 0;
+  CRL_CUDA(cudaMemcpyAsync(&c, e->P.counters + 2, sizeof(c), cudaMemcpyDeviceToHost, e->stream));
+  CRL_CUDA(cudaStreamSynchronize(e->stream));
+  *reused_host = c;
+  return CRL_OK;
+}
+
 int crl_mcts_begin_move(crl_engine* e) {
   CHECK_ENGINE(e);
-  int rc = tree_begin_move(e, nullptr);
+  int rc = tree_begin_move(e, nullptr, e->reuse);
   if (rc) return rc;
   e->tree_ready = true;
   return CRL_OK;

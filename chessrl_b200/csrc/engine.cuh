@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/chessrl_b200.h"
@@ -65,8 +66,10 @@ struct crl_engine_impl {
   // CUDA graph of one lockstep simulation (replayed n_sims times); rebuilt when the evaluator changes
   bool own_stream = false;
   bool use_graph = true;
-  cudaGraphExec_t sim_graph = nullptr;
-  unsigned long long sim_graph_key = 0;
+  cudaGraphExec_t sim_graph[2] = {nullptr, nullptr};   // one per tree parity (the pools swap roles under evaluation reuse)
+  unsigned long long sim_graph_key[2] = {0, 0};
+  int tree_parity = 0;
+  bool reuse = false;              // crl_set_reuse: expansions take evaluations from the previous move's tree
   long long sim_graph_launches = 0;
   bool capturing = false;
   // accounting
@@ -133,7 +136,7 @@ int launch_gather_moves(crl_engine_impl* e, const int* lanes, int n, int cap, u1
 int launch_game_info(crl_engine_impl* e, int first, int n, u16* legal, int* n_legal);
 int launch_game_moves(crl_engine_impl* e, const u16* moves_per_game /*[G]*/, u8* accepted /*[G] or null*/);
 int launch_eval_batch(crl_engine_impl* e, int which_mode);   // encodes eval_list rows and runs the evaluator
-int tree_begin_move(crl_engine_impl* e, const u8* mask_dev);
+int tree_begin_move(crl_engine_impl* e, const u8* mask_dev, bool use_prev);
 int tree_simulate(crl_engine_impl* e, int n_sims, int K);
 int tree_run_steps(crl_engine_impl* e, int n_steps, int K);
 int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev);

@@ -102,10 +102,13 @@ __device__ __forceinline__ int analyse_position_warp(const Pools& P, int g, cons
 
 // expand_child (tree_core.cuh; mctree.py:241-244) run by the whole warp: uniform reads and arithmetic in every lane,
 // the node's fields written by lane 0, the legal moves of P1 generated cooperatively into the slot's move row.
-__device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot, int parent, int lane, int* out_child) {
+__device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot, int parent, int lane, int* out_child,
+                                                 int* out_twin = nullptr) {
   NodeRec& pn = P.nodes[(long long)g * P.NN + parent];
   const int child = P.g_nnodes[g];
   const int k = pn.n_exp;
+  const int twin = twin_of_child(P, g, pn, k);                 // same node in the previous move's tree, or -1
+  if (out_twin) *out_twin = twin;
   const long long ebase = (long long)g * P.EA + pn.edge0;
   const u16 mv = P.e_move[ebase + (pn.n_legal - 1 - k)];       // unexpanded_actions.pop(): last legal move first
   Board b = load_rec(pn.p2);
@@ -129,6 +132,9 @@ __device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot
     cn.n_legal = 0;
     cn.edge0 = 0;
     cn.pending = 0;
+    cn.prev = twin;
+    cn.v = 0.f;
+    cn.evald = 0;
     P.e_child[ebase + k] = child;
     P.e_visits[ebase + k] = 0;
     P.e_value[ebase + k] = 0.0;
@@ -203,8 +209,27 @@ __device__ __forceinline__ int reply_child_warp(const Pools& P, int g, int slot,
   return KIND_EVAL_LEAF;
 }
 
+// adopt_evaluation (tree_core.cuh) by the whole warp: the twin's value and its children's priors become the node's
+__device__ __forceinline__ bool adopt_evaluation_warp(const Pools& P, int g, int node, int twin, int lane) {
+  NodeRec& n = P.nodes[(long long)g * P.NN + node];
+  const NodeRec& t = P.nodes_prev[(long long)g * P.NN + twin];
+  const int L = n.n_legal;
+  if (t.result != RESULT_NONE || t.n_legal != L) return false;
+  const long long dst = (long long)g * P.EA + n.edge0, src = (long long)g * P.EA + t.edge0;
+  for (int i = lane; i < L; i += 32) P.e_prior[dst + i] = P.e_prior_prev[src + i];
+  if (lane == 0) {
+    n.v = t.v;
+    n.evald = 1;
+  }
+  return true;
+}
+
 // (7 blocks = 28 warps per SM: 148 x 28 = 4,144 resident warps, so 4,096 games run as ONE wave instead of 1.5)
-__global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P) {
+// list_b / n_b: batch B of this simulation (node states to evaluate), which k_reply fills; with evaluation reuse a warp
+// whose new child has a twin in the previous tree plays the twin's reply at once -- no batch-A row -- and normally takes
+// the twin's value and priors as well, so that simulation runs without the network.
+__global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, int* list_b, int* n_b) {
+  __shared__ u16 s_gen[TREE_WARPS][MAX_MOVES];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= P.G) return;
@@ -221,8 +246,39 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P) {
     }
     return;
   }
-  int child;
-  const int kind = expand_child_warp(P, g, g, node, lane, &child);
+  int child, twin;
+  int kind = expand_child_warp(P, g, g, node, lane, &child, &twin);
+  if (kind == KIND_NEED_REPLY && twin >= 0) {
+    const u16 reply = P.nodes_prev[(long long)g * P.NN + twin].reply;
+    const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
+    const int n1 = P.s_nmoves[g];
+    int pick = 0x7fffffff;
+    for (int i = lane; i < n1; i += 32)
+      if (moves1[i] == reply) pick = i;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) pick = min(pick, __shfl_xor_sync(0xffffffffu, pick, off));
+    if (pick < n1) {                               // always, unless the pools were tampered with: then evaluate as usual
+      kind = reply_child_warp(P, g, g, child, pick, lane, s_gen[threadIdx.x >> 5]);
+      int reused = 1;
+      if (kind == KIND_EVAL_LEAF) {
+        __syncwarp();
+        if (adopt_evaluation_warp(P, g, child, twin, lane)) {
+          kind = KIND_EVAL_REUSED;
+          reused = 2;
+        }
+      }
+      if (lane != 0) return;
+      atomicAdd((unsigned long long*)&P.counters[2], (unsigned long long)reused);
+      P.s_node[g] = child;
+      P.s_kind[g] = kind;
+      if (kind == KIND_EVAL_LEAF) {                // (defensive) the twin's evaluation did not fit: run it
+        const int rb = atomicAdd(n_b, 1);
+        list_b[rb] = g;
+        P.s_row[g] = rb;
+      }
+      return;
+    }
+  }
   if (lane != 0) return;
   P.s_node[g] = child;
   P.s_kind[g] = kind;
@@ -294,7 +350,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const flo
     const int node = P.s_node[slot];
     const int kind = P.s_kind[slot];
     if (kind == KIND_IDLE) continue;          // node pool overflow (flagged in P.err)
-    const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+    NodeRec& n = P.nodes[(long long)g * P.NN + node];
     double v;
     if (kind == KIND_EVAL_LEAF) {
       const int row = P.s_row[slot];
@@ -305,7 +361,12 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const flo
         const u16 m = P.e_move[ebase + i];
         P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
       }
-      v = (double)value[row];
+      const float vf = value[row];
+      v = (double)vf;
+      if (lane == 0) {
+        n.v = vf;          // kept for the next move's search (evaluation reuse)
+        n.evald = 1;
+      }
     } else {
       v = (double)n.result;
     }
@@ -385,7 +446,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* _
   if (!game_running(P, g) || P.s_kind[g] == KIND_IDLE) return;
   const int node = P.s_node[g];
   const int kind = P.s_kind[g];
-  const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+  NodeRec& n = P.nodes[(long long)g * P.NN + node];
   double v;
   if (kind == KIND_EVAL_LEAF) {
     const int row = P.s_row[g];
@@ -396,7 +457,14 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* _
       const u16 m = P.e_move[ebase + i];
       P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
     }
-    v = (double)value[row];                                   // float(v) of a float32 (predict_worker.py:111)
+    const float vf = value[row];
+    v = (double)vf;                                           // float(v) of a float32 (predict_worker.py:111)
+    if (lane == 0) {
+      n.v = vf;                                               // kept for the next move's search (evaluation reuse)
+      n.evald = 1;
+    }
+  } else if (kind == KIND_EVAL_REUSED) {
+    v = (double)n.v;                                          // the same float32 the previous search got from the network
   } else {
     v = (double)n.result;                                     // terminal: Game.get_result (mctree.py:268)
   }
@@ -406,13 +474,19 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* _
 }
 
 // Tree(root): build node 0 of every running game and queue it for evaluation
-__global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __restrict__ mask) {
+__global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __restrict__ mask, int use_prev) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= P.G) return;
   P.s_kind[g] = KIND_IDLE;
-  if (!game_running(P, g) || (mask && !mask[g])) return;
-  root_init(P, g);
+  if (!game_running(P, g) || (mask && !mask[g])) {
+    if (use_prev) P.g_prev_root[g] = -1;
+    return;
+  }
   P.s_node[g] = 0;
+  if (!root_init(P, g, use_prev != 0)) {       // priors taken over from the previous tree: no evaluation
+    atomicAdd((unsigned long long*)&P.counters[2], 1ull);
+    return;
+  }
   int row = atomicAdd(P.eval_n, 1);
   P.eval_list[row] = g;
   P.s_row[g] = row;
@@ -441,6 +515,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, const float
   if (root.n_legal > 0) mv = moves[argmax_legal(policy + (long long)r * CRL_N_LABELS, label_of, moves, root.n_legal)];
   picks[g] = mv;
   game_move(P, g, mv);
+  P.g_prev_root[g] = -1;
 }
 
 // ---- game records -------------------------------------------------------------------------------------
@@ -462,6 +537,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_games_replay(Pools P, int first,
   P.g_nmoves[g] = 0;
   P.g_active[g] = 1;
   P.g_nnodes[g] = 0;
+  P.g_prev_root[g] = -1;
   game_refresh(P, g, nullptr, nullptr);
   // optional: the record after every ACCEPTED move (AoS, record j of game i at records[(i*(stride+1) + j)*9]);
   // record 0 is the start position.  This is what Board.copy() + pop() walks back through (netencoder.py:58-67).
@@ -495,6 +571,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_game_moves(Pools P, const u16* _
   if (g >= P.G) return;
   int ok = 0;
   if (P.g_active[g] && mv[g] != MOVE_NONE) ok = game_move(P, g, mv[g]);
+  if (ok) P.g_prev_root[g] = -1;             // the position no longer is a node of the last tree
   if (accepted) accepted[g] = (u8)ok;
 }
 
@@ -530,10 +607,17 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __res
   }
   out_moves[2 * g] = m0;
   out_moves[2 * g + 1] = m1;
+  int next_root = -1;
   if (apply && P.g_active[g] && k >= 0) {
-    game_move(P, g, m0);       // selfplay.py:77-78: Game.move silently rejects an illegal first move
-    game_move(P, g, m1);
+    const int ok0 = game_move(P, g, m0);       // selfplay.py:77-78: Game.move silently rejects an illegal first move
+    const int ok1 = game_move(P, g, m1);
+    // the game now stands where the chosen child stands: the next search may take evaluations from this tree
+    if (ok0 && ok1 && k < root.n_exp) {
+      const int c = P.e_child[(long long)g * P.EA + root.edge0 + k];
+      if (P.nodes[(long long)g * P.NN + c].reply == m1 && P.nodes[(long long)g * P.NN + c].move == m0) next_root = c;
+    }
   }
+  P.g_prev_root[g] = next_root;
 }
 
 // ---- launchers ----------------------------------------------------------------------------------------
@@ -572,14 +656,23 @@ static int use_list(crl_engine_impl* e, int which) {
 }
 
 // Tree(root) for every running game (or the masked subset): node 0, its legal moves, its priors
-int tree_begin_move(crl_engine_impl* e, const u8* mask_dev) {
+// use_prev: a new move search of ALL lanes with evaluation reuse on -- the pools swap roles first, so the tree just
+// searched becomes the previous tree the new one looks its twins up in
+int tree_begin_move(crl_engine_impl* e, const u8* mask_dev, bool use_prev) {
+  if (use_prev) {
+    std::swap(e->P.nodes, e->P.nodes_prev);
+    std::swap(e->P.e_prior, e->P.e_prior_prev);
+    std::swap(e->P.e_child, e->P.e_child_prev);
+    e->tree_parity ^= 1;
+  }
   CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
   use_list(e, 0);
   e->P.K = 1;                 // root batch: one row per game
+  e->P.reuse = e->reuse ? 1 : 0;
   e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
-    k_root_init<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mask_dev);
+    k_root_init<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mask_dev, use_prev ? 1 : 0);
     CRL_CUDA(cudaGetLastError());
   }
   int rc = launch_eval_batch(e, 0);
@@ -597,10 +690,11 @@ static int one_simulation(crl_engine_impl* e) {
   CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
   use_list(e, 0);
   e->P.K = 1;
+  e->P.reuse = e->reuse ? 1 : 0;
   e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
-    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
+    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   int rc = launch_eval_batch(e, 1);
@@ -628,6 +722,7 @@ static int one_wave(crl_engine_impl* e, int K) {
   CRL_CUDA(cudaMemsetAsync(e->d_n, 0, 2 * sizeof(int), e->stream));
   use_list(e, 0);
   e->P.K = K;
+  e->P.reuse = 0;             // the wave schedule evaluates everything (twins are looked up in the exact schedule only)
   e->cur_rows = e->G * K;
   {
     LaunchScope ls(e, KC_TREE);
@@ -706,12 +801,16 @@ int tree_run_steps(crl_engine_impl* e, int n_sims, int K) {
     }
     return CRL_OK;
   }
+  // the kernel parameters (pool pointers included) are baked into the captured graph; with evaluation reuse the tree
+  // pools swap roles at every move, so there is one graph per parity
+  const int par = e->tree_parity & 1;
   const unsigned long long key = 1ull + (unsigned long long)e->eval_kind + 2ull * (unsigned long long)e->eval_bits +
-                                 64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull) + 0x100000000ull * (unsigned long long)K;
-  if (e->sim_graph == nullptr || e->sim_graph_key != key) {
-    if (e->sim_graph) {
-      cudaGraphExecDestroy(e->sim_graph);
-      e->sim_graph = nullptr;
+                                 64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull) + 0x100000000ull * (unsigned long long)K +
+                                 (e->reuse ? 0x8000000000000000ull : 0ull);
+  if (e->sim_graph[par] == nullptr || e->sim_graph_key[par] != key) {
+    if (e->sim_graph[par]) {
+      cudaGraphExecDestroy(e->sim_graph[par]);
+      e->sim_graph[par] = nullptr;
     }
     // run one simulation eagerly first: it creates whatever host-side state the launchers cache (tensor maps)
     int rc = one_step(e, K);
@@ -734,19 +833,19 @@ int tree_run_steps(crl_engine_impl* e, int n_sims, int K) {
       return rc;
     }
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
-    ce = cudaGraphInstantiate(&e->sim_graph, graph, 0);
+    ce = cudaGraphInstantiate(&e->sim_graph[par], graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaGraphInstantiate");
-    e->sim_graph_key = key;
+    e->sim_graph_key[par] = key;
   }
-  for (int s = 0; s < n_sims; ++s) CRL_CUDA(cudaGraphLaunch(e->sim_graph, e->stream));
+  for (int s = 0; s < n_sims; ++s) CRL_CUDA(cudaGraphLaunch(e->sim_graph[par], e->stream));
   e->launches += (long long)n_sims * e->sim_graph_launches;
   return CRL_OK;
 }
 
 int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev) {
   CRL_CUDA(cudaMemsetAsync(picks_dev, 0xFF, sizeof(u16) * e->G, e->stream));
-  int rc = tree_begin_move(e, mask_dev);   // root_init + evaluation of the current positions
+  int rc = tree_begin_move(e, mask_dev, false);   // root_init + evaluation of the current positions
   if (rc != CRL_OK) return rc;
   LaunchScope ls(e, KC_TREE);
   k_policy_move<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, picks_dev);

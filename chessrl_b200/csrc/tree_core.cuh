@@ -25,7 +25,8 @@
 namespace crl {
 
 enum { HIST_RING = 8, KEY_RING = 128, MAX_GAME_PLIES = 2048 };
-enum { KIND_IDLE = 0, KIND_TERMINAL = 1, KIND_NEED_REPLY = 2, KIND_NEW_TERMINAL = 3, KIND_EVAL_LEAF = 4 };
+enum { KIND_IDLE = 0, KIND_TERMINAL = 1, KIND_NEED_REPLY = 2, KIND_NEW_TERMINAL = 3, KIND_EVAL_LEAF = 4,
+       KIND_EVAL_REUSED = 5 };   // new leaf whose value / priors came from its twin in the previous move's tree
 enum { ERR_NODE_OVERFLOW = 1, ERR_EDGE_OVERFLOW = 2, ERR_PLY_OVERFLOW = 4 };
 
 struct NodeRec {
@@ -42,6 +43,10 @@ struct NodeRec {
   u8 slot;        // index among the parent's children (creation order)
   u8 has_p1;      // 0 for the root
   u8 pending;     // wave mode: created in the current wave, its reply (network evaluation of p1) is not known yet
+  // --- evaluation reuse across consecutive searches of one game (see "evaluation reuse" below) ---
+  int prev;       // node of the PREVIOUS move's tree that is this same node (same game, same path), -1 if none
+  float v;        // network value of p2 (valid when evald)
+  u8 evald;       // 1 once the node has been evaluated: reply, n_legal, v and its children's priors are final
 };
 
 struct Pools {
@@ -67,6 +72,12 @@ struct Pools {
   u8* e_vloss;      // [G][EA] Node.vloss of the child on this edge (mctree.py:36, 226-227, 292-293); 0 outside a wave
   int* r_visits;    // [G]
   double* r_value;  // [G]
+  // --- evaluation reuse: the tree of the previous move search (the pools swap roles at every crl_mcts_begin_move) ---
+  int reuse;            // 1: expansions look their twin up in the previous tree (exact schedule, K = 1, only)
+  NodeRec* nodes_prev;  // [G][NN]
+  float* e_prior_prev;  // [G][EA]
+  int* e_child_prev;    // [G][EA]
+  int* g_prev_root;     // [G] node of the previous tree whose state is the game's current position, -1 = none
   // --- per-simulation scratch: one SLOT per in-flight simulation, slot = g*K + j (K = 1: slot = game) ---
   int K;            // in-flight simulations per game of the kernels being launched (1 = the exact threads=1 schedule)
   int* s_node;      // [G*K] selected node / new child
@@ -79,7 +90,7 @@ struct Pools {
   int* eval_list;   // [G*K] slot of every batch row
   int* eval_n;      // [1]
   int* err;         // [1] ERR_* flags
-  long long* counters;  // [0] simulations [1] evaluations
+  long long* counters;  // [0] simulations [1] evaluations run [2] evaluations taken from the previous tree instead
 };
 
 CRL_HD Board load_soa(const u64* base, long long stride, long long i) {
@@ -254,6 +265,44 @@ CRL_HD void vloss_add(const Pools& P, int g, int node, int d) {
   P.e_vloss[e] = (u8)((int)P.e_vloss[e] + d);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// evaluation reuse.  The reference builds a fresh tree for every move (agentdistributed.py:61-63), so the network
+// is asked again about positions the previous search already evaluated: after the game has played (our move,
+// reply) of root child c, the new root IS c, and every node below c in the old tree is the same position reached
+// by the same plies -- same history planes, same network input, same output.  The new search still builds its
+// tree from scratch (all statistics start at zero, the selection order is the reference's); only the two network
+// evaluations of an expansion are looked up instead of run when the old tree holds the node's TWIN.  Twins are
+// found without hashing: children are created in a fixed order (last legal move first), so the child the new
+// node creates at slot k is the twin of the child at slot k of the parent's twin.  Results are bit-identical by
+// construction (tests: reuse on / off plays the same games with the same root statistics).
+// ---------------------------------------------------------------------------------------------------
+CRL_HD int twin_of_child(const Pools& P, int g, const NodeRec& parent, int k) {
+  if (!P.reuse || parent.prev < 0) return -1;
+  const NodeRec& on = P.nodes_prev[(long long)g * P.NN + parent.prev];
+  if (k >= on.n_exp) return -1;
+  const int oc = P.e_child_prev[(long long)g * P.EA + on.edge0 + k];
+  return P.nodes_prev[(long long)g * P.NN + oc].evald ? oc : -1;
+}
+
+// index of `mv` in a move list, -1 if absent
+CRL_HD int find_move(const u16* moves, int n, u16 mv) {
+  for (int i = 0; i < n; ++i)
+    if (moves[i] == mv) return i;
+  return -1;
+}
+
+// hand the twin's value and its children's priors to `node` (just built by reply_child); false if they do not fit
+CRL_HD bool adopt_evaluation(const Pools& P, int g, int node, int twin) {
+  NodeRec& n = P.nodes[(long long)g * P.NN + node];
+  const NodeRec& t = P.nodes_prev[(long long)g * P.NN + twin];
+  if (t.result != RESULT_NONE || t.n_legal != n.n_legal) return false;
+  const long long dst = (long long)g * P.EA + n.edge0, src = (long long)g * P.EA + t.edge0;
+  for (int i = 0; i < n.n_legal; ++i) P.e_prior[dst + i] = P.e_prior_prev[src + i];
+  n.v = t.v;
+  n.evald = 1;
+  return true;
+}
+
 // generate the legal moves of `b`, its transposition key and Game.get_result, given where it sits
 CRL_HD int analyse_position(const Pools& P, int g, const Board& b, Cursor at, u16* moves, int* n_moves, u64* key) {
   StoreSink sink{moves, 0};
@@ -294,6 +343,9 @@ CRL_HD int expand_child(const Pools& P, int g, int slot, int parent, int* out_ch
   cn.n_legal = 0;
   cn.edge0 = 0;
   cn.pending = 0;
+  cn.prev = twin_of_child(P, g, pn, k);
+  cn.v = 0.f;
+  cn.evald = 0;
   P.e_child[ebase + k] = child;
   P.e_visits[ebase + k] = 0;
   P.e_value[ebase + k] = 0.0;
@@ -477,8 +529,10 @@ CRL_HD int game_move(const Pools& P, int g, u16 mv) {
   return 1;
 }
 
-// Tree(root) (mctree.py:104-111): node 0 = copy of the current game position, visits = 1
-CRL_HD int root_init(const Pools& P, int g) {
+// Tree(root) (mctree.py:104-111): node 0 = copy of the current game position, visits = 1.
+// Returns 1 if the root's policy has to be evaluated, 0 if its priors were taken over from its twin in the previous
+// tree (use_prev: the pools have just swapped roles and g_prev_root names the node the game moved to).
+CRL_HD int root_init(const Pools& P, int g, bool use_prev = false) {
   Board b = load_soa(P.g_cur, P.G, g);
   NodeRec& r = P.nodes[(long long)g * P.NN];
   store_rec(r.p2, b);
@@ -491,6 +545,9 @@ CRL_HD int root_init(const Pools& P, int g) {
   r.n_exp = 0;
   r.edge0 = 0;
   r.pending = 0;
+  r.prev = -1;
+  r.v = 0.f;
+  r.evald = 0;
   int ply = meta_ply(b.meta);
   r.key2 = r.key1 = P.g_keys[(long long)(ply % KEY_RING) * P.G + g];
   r.result = P.g_result[g];
@@ -502,6 +559,8 @@ CRL_HD int root_init(const Pools& P, int g) {
   P.g_nedges[g] = sink.n;
   P.r_visits[g] = 1;
   P.r_value[g] = 0.0;
+  const int twin = (use_prev && P.reuse) ? P.g_prev_root[g] : -1;
+  P.g_prev_root[g] = -1;              // consumed: it named a node of the pool that is the previous tree only now
   if (sink.n > P.EA) {
     *P.err |= ERR_EDGE_OVERFLOW;
     r.n_legal = 0;
@@ -509,7 +568,18 @@ CRL_HD int root_init(const Pools& P, int g) {
   }
   long long ebase = (long long)g * P.EA;
   for (int i = 0; i < sink.n; ++i) P.e_move[ebase + i] = moves[i];
-  return sink.n;
+  if (twin >= 0) {
+    const NodeRec& t = P.nodes_prev[(long long)g * P.NN + twin];
+    bool same = t.evald && t.result == RESULT_NONE && t.n_legal == sink.n;
+    for (int k = 0; k < 9; ++k) same = same && t.p2[k] == r.p2[k];
+    if (same) {                       // the game really is where that node stands: its priors are the root's priors
+      const long long src = (long long)g * P.EA + t.edge0;
+      for (int i = 0; i < sink.n; ++i) P.e_prior[ebase + i] = P.e_prior_prev[src + i];
+      r.prev = twin;
+      return 0;
+    }
+  }
+  return 1;
 }
 
 }  // namespace crl

@@ -316,6 +316,12 @@ class Engine:
     def mcts_begin_move(self):
         check(self.lib.crl_mcts_begin_move(self.h))
 
+    def set_reuse(self, enable=True):
+        """Evaluation reuse across consecutive move searches (include/chessrl_b200.h crl_set_reuse): expansions take the
+        reply / value / priors of nodes the previous move's search already evaluated; results are bit-identical."""
+        check(self.lib.crl_set_reuse(self.h, int(bool(enable))))
+        self.reuse = bool(enable)
+
     def mcts_simulate(self, n_sims, inflight=1):
         check(self.lib.crl_mcts_simulate(self.h, int(n_sims), int(inflight)))
 
@@ -360,7 +366,9 @@ class Engine:
     def counters(self):
         c = np.zeros(3, dtype=np.int64)
         check(self.lib.crl_counters_host(self.h, _np(c, ctypes.c_int64)))
-        return {"simulations": int(c[0]), "evaluations": int(c[1]), "launches": int(c[2])}
+        r = np.zeros(1, dtype=np.int64)
+        check(self.lib.crl_reuse_count_host(self.h, _np(r, ctypes.c_int64)))
+        return {"simulations": int(c[0]), "evaluations": int(c[1]), "launches": int(c[2]), "reused_evaluations": int(r[0])}
 
     def profile(self, enable):
         check(self.lib.crl_profile(self.h, int(bool(enable))))

@@ -97,14 +97,19 @@ class LockstepSelfPlay:
     policy-argmax move (selfplay.py:68-70).  noise=True draws Dirichlet noise from numpy's legacy global RNG in
     game-index order, once per game per move (the reference draws once per move of its single game).
     inflight: simulations in flight per game (the reference's `threads`; needs Engine(max_inflight >= inflight)).
+    reuse: None leaves the engine as it is; True / False switches its evaluation reuse (Engine.set_reuse): a search
+    takes the evaluations of nodes the previous move's search of the same game already ran -- same games, fewer
+    network evaluations (exact schedule only; ignored for inflight > 1).
 
     Host round trips per move: root statistics, the commit, and one status read (plies + results) that harvest /
     running / the next step's move pick all reuse; harvest and refill are one batched call each whatever the number
     of lanes involved.
     """
 
-    def __init__(self, engine, n_games=None, sims=900, noise=True, refill=False, inflight=1):
+    def __init__(self, engine, n_games=None, sims=900, noise=True, refill=False, inflight=1, reuse=None):
         self.e = engine
+        if reuse is not None:
+            engine.set_reuse(bool(reuse) and int(inflight) == 1)
         self.n = engine.max_games if n_games is None else n_games
         self.sims = sims
         self.inflight = int(inflight)

@@ -90,7 +90,7 @@ class LockstepRun:
     """
 
     def __init__(self, model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
-                 threads=1, evaluator=None, engine=None):
+                 threads=1, evaluator=None, engine=None, reuse=True):
         import time
         from ._lib import EVAL_HASH, EVAL_NET
         from .engine import Engine
@@ -115,7 +115,9 @@ class LockstepRun:
             self.eng.set_evaluator(EVAL_HASH, int(evaluator[1]), int(evaluator[2]))
         self._rng = random.Random(seed)
         self._colors = []                                  # colour of game i, drawn like selfplay.py:62
-        self.sp = LockstepSelfPlay(self.eng, n_games=lanes, sims=sims, noise=noise, inflight=threads)
+        # reuse: evaluations of the previous move's search are looked up instead of run again (crl_set_reuse): the games
+        # are the same move for move, the network runs less often
+        self.sp = LockstepSelfPlay(self.eng, n_games=lanes, sims=sims, noise=noise, inflight=threads, reuse=reuse)
         # the engine's move lists hold 2,048 plies per game: a game that gets there is stored unfinished instead of
         # failing the whole run (the fifty-move claim ends games long before that in practice)
         self.cap = 2040 if max_moves is None else min(2040, 2 * max_moves)
@@ -172,7 +174,8 @@ class LockstepRun:
         c1 = self.eng.counters()
         sims = c1["simulations"] - self.c0["simulations"]
         return {"steps": self.steps, "moves": self.sp.moves_played, "seconds": self._time.perf_counter() - self.t0,
-                "simulations": sims, "evaluations": c1["evaluations"] - self.c0["evaluations"], "lanes": self.lanes,
+                "simulations": sims, "evaluations": c1["evaluations"] - self.c0["evaluations"],
+                "reused_evaluations": c1.get("reused_evaluations", 0) - self.c0.get("reused_evaluations", 0), "lanes": self.lanes,
                 "games_finished": self.finished_games, "refills": self.refills,
                 "lane_occupancy": sims / max(1, self.steps * self.lanes * self.sims)}
 
@@ -193,15 +196,16 @@ class LockstepRun:
 
 
 def play_games_lockstep(model, n_games, sims=900, lanes=None, noise=True, device=None, seed=None, max_moves=None,
-                        threads=1, evaluator=None, stats=None):
+                        threads=1, evaluator=None, stats=None, reuse=True):
     """`n_games` games in lockstep, `lanes` at a time; returns a DatasetGame in game-start order.
 
     The per-move host work is the numpy move policy only.  max_moves caps the agent moves of a game (it is then stored
     unfinished, result None).  evaluator: None = the network with `model`'s weights; ("hash", seed, bits) = the
     deterministic test evaluator.  stats: optional dict that receives steps / moves / simulations / seconds / lane
-    occupancy of the run."""
+    occupancy of the run.  reuse: take evaluations from the previous move's tree where it holds the same node (same
+    games either way; include/chessrl_b200.h crl_set_reuse)."""
     run = LockstepRun(model, n_games, sims=sims, lanes=lanes, noise=noise, device=device, seed=seed, max_moves=max_moves,
-                      threads=threads, evaluator=evaluator)
+                      threads=threads, evaluator=evaluator, reuse=reuse)
     try:
         while run.advance():
             pass
@@ -224,6 +228,9 @@ def main(argv=None):
                         help="games stepped in lockstep per GPU (default: about four games per lane in whole tower rounds)")
     parser.add_argument('--max-moves', type=int, default=None, help="cap on the agent's moves per game (stored unfinished)")
     parser.add_argument('--no-train', action='store_true', default=False)
+    parser.add_argument('--no-reuse', action='store_true', default=False,
+                        help="evaluate every position of every search (default: evaluations of the previous move's "
+                             "search are reused; the games are identical either way)")
     args = parser.parse_args(argv)
 
     logger = Logger.get_instance()
@@ -246,7 +253,8 @@ def main(argv=None):
     stats = {}
     lanes = args.lanes if args.lanes is not None else default_lanes(share)
     data = (play_games_lockstep(agent.model, share, sims=args.sims, lanes=lanes, device=local_rank,
-                                threads=args.threads, max_moves=args.max_moves, stats=stats) if share else DatasetGame())
+                                threads=args.threads, max_moves=args.max_moves, stats=stats,
+                                reuse=not args.no_reuse) if share else DatasetGame())
     if stats:
         full = max(1, stats["steps"] * stats["lanes"] * args.sims)
         logger.info("rank %d: %d games, %d agent moves in %d lockstep steps, %.1f s: %.0f simulations/s, lane occupancy %.1f %%"

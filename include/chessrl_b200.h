@@ -197,6 +197,20 @@ int crl_games_policy_move_host(crl_engine* e, const uint8_t* mask_host, uint16_t
 /* Tree(root) (mctree.py:104-111): a fresh tree per running game rooted at its current position,
  * root.visits = 1, root evaluated once for its children's priors. */
 int crl_mcts_begin_move(crl_engine* e);
+/* Evaluation reuse across consecutive move searches of a game (off by default).  The reference builds a new tree for
+ * every move (agentdistributed.py:61-63) and therefore asks the network again about positions its previous search
+ * already evaluated: once the game has played (our move, reply) of root child c (selfplay.py:77-78), the new root IS c
+ * and everything below c in the old tree is the same position reached by the same plies -- same history planes
+ * (netencoder.py:47-69), same network input, same output.  With reuse on, the engine keeps the previous tree (a second
+ * set of node / prior / child pools that swaps roles at every crl_mcts_begin_move) and an expansion whose node has a
+ * TWIN there takes the opponent's reply, the value and the children's priors from it instead of running the two
+ * evaluations.  The new tree itself is built from scratch exactly as before -- statistics start at zero, the schedule
+ * is the reference's -- so visit counts, value sums and the games played are bit-identical with reuse on and off.
+ * Twins are linked when crl_mcts_commit_host(apply = 1) plays a root child's two plies; any other change of a game
+ * (set / restart / play / policy move) unlinks it.  Exact schedule (inflight = 1) only; waves evaluate everything.
+ * crl_reuse_count_host: evaluations taken from the previous tree so far (crl_counters_host counts only those run). */
+int crl_set_reuse(crl_engine* e, int enable);
+int crl_reuse_count_host(crl_engine* e, int64_t* reused_host);
 /* n_sims x SelfPlayTree.explore_tree (mctree.py:200-214) for every running game in lockstep.
  * inflight = 1: the deterministic threads=1 schedule.
  * inflight = K > 1 (<= max_inflight): WAVES of up to K simulations per game = one legal schedule of the reference's

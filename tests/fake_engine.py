@@ -32,6 +32,9 @@ class FakeEngine:
     def set_evaluator(self, kind, seed=0, policy_bits=24):
         pass
 
+    def set_reuse(self, enable=True):
+        pass
+
     def close(self):
         pass
 

@@ -113,6 +113,7 @@ uint64_t hs_perft(const uint64_t* rec, int depth, int bulk) {
 #include "../../chessrl_b200/csrc/tree_core.cuh"
 #include "../../chessrl_b200/csrc/hash_eval.cuh"
 #include <stdlib.h>
+#include <utility>
 #include <vector>
 
 struct HostTree {
@@ -148,6 +149,12 @@ void* hs_tree_new(int NN, int EA, const int16_t* label_of) {
   P.e_vloss = (u8*)calloc(EA, 1);
   P.r_visits = (int*)calloc(1, 4);
   P.r_value = (double*)calloc(1, 8);
+  P.reuse = 0;
+  P.nodes_prev = (NodeRec*)calloc(NN, sizeof(NodeRec));
+  P.e_prior_prev = (float*)calloc(EA, 4);
+  P.e_child_prev = (int*)calloc(EA, 4);
+  P.g_prev_root = (int*)calloc(1, 4);
+  P.g_prev_root[0] = -1;
   P.s_node = (int*)calloc(HS_KMAX, 4);
   P.s_kind = (int*)calloc(HS_KMAX, 4);
   P.s_moves = (u16*)calloc(HS_KMAX * MAX_MOVES, 2);
@@ -170,13 +177,22 @@ int hs_game_set(void* h, const uint64_t* start, const uint16_t* moves, int n) {
   Pools& P = t->P;
   for (int k = 0; k < 9; ++k) P.g_cur[k] = start[k];
   P.g_nmoves[0] = 0;
+  P.g_prev_root[0] = -1;
   game_refresh(P, 0, nullptr, nullptr);
   int ok = 0;
   for (int i = 0; i < n; ++i) ok += game_move(P, 0, moves[i]);
   return ok;
 }
-int hs_game_move(void* h, uint16_t mv) { return game_move(((HostTree*)h)->P, 0, mv); }
+int hs_game_move(void* h, uint16_t mv) {
+  Pools& P = ((HostTree*)h)->P;
+  const int ok = game_move(P, 0, mv);
+  if (ok) P.g_prev_root[0] = -1;
+  return ok;
+}
 int hs_game_result(void* h) { return ((HostTree*)h)->P.g_result[0]; }
+void hs_cur_record(void* h, uint64_t* out9) {
+  for (int k = 0; k < 9; ++k) out9[k] = ((HostTree*)h)->P.g_cur[k];
+}
 
 static void host_eval(HostTree* t, const u64* rec, uint64_t seed, int bits, float* value) {
   Board b = load_rec(rec);
@@ -185,14 +201,25 @@ static void host_eval(HostTree* t, const u64* rec, uint64_t seed, int bits, floa
   *value = hash_value(hh);
 }
 
-int hs_search(void* h, int sims, uint64_t seed, int bits) {
+// reuse != 0: evaluation reuse (tree_core.cuh "evaluation reuse") -- the pools swap roles first and expansions look
+// their twin up in the tree of the previous hs_search call, as crl_mcts_begin_move / k_select_expand do on the device.
+// Returns the number of evaluations RUN (low 24 bits) and the error flags.
+static int hs_search_impl(void* h, int sims, uint64_t seed, int bits, int reuse) {
   HostTree* t = (HostTree*)h;
   Pools& P = t->P;
   float v;
-  root_init(P, 0);
-  host_eval(t, P.nodes[0].p2, seed, bits, &v);
-  store_priors(P, 0, 0, t->policy.data(), t->label_of.data());
-  int evals = 1;
+  P.reuse = reuse ? 1 : 0;
+  if (reuse) {
+    std::swap(P.nodes, P.nodes_prev);
+    std::swap(P.e_prior, P.e_prior_prev);
+    std::swap(P.e_child, P.e_child_prev);
+  }
+  int evals = 0;
+  if (root_init(P, 0, reuse != 0)) {
+    host_eval(t, P.nodes[0].p2, seed, bits, &v);
+    store_priors(P, 0, 0, t->policy.data(), t->label_of.data());
+    ++evals;
+  }
   for (int s = 0; s < sims; ++s) {
     int node, term;
     select_descend(P, 0, [&](const NodeRec& n) { return best_edge_serial(P, 0, n); }, &node, &term);
@@ -203,15 +230,26 @@ int hs_search(void* h, int sims, uint64_t seed, int bits) {
       int child;
       int kind = expand_child(P, 0, 0, node, &child);
       node = child;
+      const int twin = P.nodes[child].prev;
+      bool adopted = false;
       if (kind == KIND_NEED_REPLY) {
-        host_eval(t, P.nodes[child].p1, seed, bits, &v);
-        ++evals;
-        kind = reply_child(P, 0, 0, child, t->policy.data(), t->label_of.data());
+        int pick = -1;
+        if (twin >= 0) pick = find_move(P.s_moves, P.s_nmoves[0], P.nodes_prev[twin].reply);
+        if (pick < 0) {
+          host_eval(t, P.nodes[child].p1, seed, bits, &v);
+          ++evals;
+        }
+        kind = reply_child(P, 0, 0, child, t->policy.data(), t->label_of.data(), pick);
+        if (pick >= 0 && kind == KIND_EVAL_LEAF) adopted = adopt_evaluation(P, 0, child, twin);
       }
-      if (kind == KIND_EVAL_LEAF) {
+      if (kind == KIND_EVAL_LEAF && adopted) {
+        val = (double)P.nodes[child].v;
+      } else if (kind == KIND_EVAL_LEAF) {
         host_eval(t, P.nodes[child].p2, seed, bits, &v);
         ++evals;
         store_priors(P, 0, child, t->policy.data(), t->label_of.data());
+        P.nodes[child].v = v;
+        P.nodes[child].evald = 1;
         val = (double)v;
       } else {
         val = (double)P.nodes[child].result;
@@ -220,6 +258,32 @@ int hs_search(void* h, int sims, uint64_t seed, int bits) {
     backup(P, 0, node, val);
   }
   return evals | (*P.err << 24);
+}
+int hs_search(void* h, int sims, uint64_t seed, int bits) { return hs_search_impl(h, sims, seed, bits, 0); }
+int hs_search_reuse(void* h, int sims, uint64_t seed, int bits) { return hs_search_impl(h, sims, seed, bits, 1); }
+
+// k_commit(apply = 1): play (our move, reply) of root child k and link the game to that child for the next search
+int hs_commit(void* h, int k) {
+  Pools& P = ((HostTree*)h)->P;
+  const NodeRec& root = P.nodes[0];
+  int next_root = -1, played = 0;
+  if (k >= 0 && k < root.n_exp) {
+    const int c = P.e_child[root.edge0 + k];
+    const NodeRec& cn = P.nodes[c];
+    u16 m0 = MOVE_NONE, m1 = MOVE_NONE;
+    if (cn.reply != MOVE_NONE) {
+      m0 = cn.move;
+      m1 = cn.reply;
+    } else if (P.g_nmoves[0] >= 1) {
+      m0 = P.g_moves[P.g_nmoves[0] - 1];
+      m1 = cn.move;
+    }
+    const int ok0 = game_move(P, 0, m0), ok1 = game_move(P, 0, m1);
+    played = ok0 + ok1;
+    if (ok0 && ok1 && cn.reply == m1 && cn.move == m0) next_root = c;
+  }
+  P.g_prev_root[0] = next_root;
+  return played;
 }
 
 // wave mode (K in-flight simulations): the same three phases as k_select_wave / k_reply / k_finalize_wave, serially

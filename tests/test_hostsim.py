@@ -426,3 +426,71 @@ def test_warp_cooperative_generator_equals_scalar_generator(lib):
         seen["promo"] += any(w >> 12 for w in want)
         seen["castle"] += any((w & 63) in (4, 60) and abs(((w >> 6) & 63) - (w & 63)) == 2 for w in want)
     assert seen["check"] > 1000 and seen["double"] > 20 and seen["castle"] > 300 and seen["promo"] > 500 and seen["ep"] > 200, seen
+
+
+def _root_stats(lib, t):
+    V, W, Pr = (ctypes.c_int * 256)(), (ctypes.c_double * 256)(), (ctypes.c_float * 256)()
+    M, R, Rs = (ctypes.c_uint16 * 256)(), (ctypes.c_uint16 * 256)(), (ctypes.c_int * 256)()
+    rv, rw = ctypes.c_int(), ctypes.c_double()
+    n = lib.hs_root_stats(t, V, W, Pr, M, R, Rs, ctypes.byref(rv), ctypes.byref(rw))
+    return (n, rv.value, rw.value, list(V[:n]), list(W[:n]), [float(x) for x in Pr[:n]], list(M[:n]), list(R[:n]),
+            list(Rs[:n]))
+
+
+def test_evaluation_reuse_plays_the_same_games(lib):
+    """Evaluation reuse (tree_core.cuh): a search that takes reply / value / priors from the previous move's tree builds
+    exactly the tree a search that evaluates everything builds -- root statistics (visits, value sums, priors, lines,
+    results) equal move for move along whole playouts, including games that run into mates / draws inside the tree --
+    while running far fewer evaluations whenever the game follows a well-visited child."""
+    import random
+    lib.hs_search_reuse.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_int]
+    lib.hs_commit.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.hs_game_result.argtypes = [ctypes.c_void_p]
+    tab = _label_table()
+    ta = lib.hs_tree_new(256, 256 * 220, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    tb = lib.hs_tree_new(256, 256 * 220, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_int16)))
+    rng = random.Random(5)
+    none = np.zeros(1, dtype=np.uint16)
+    moves_played = evals_plain = evals_reuse = finished = 0
+    starts = [B.STARTING_FEN] * 3 + [position_fuzz.random_fen(rng)[0] for _ in range(9)]
+    for gi, fen in enumerate(starts):
+        if O.OGame(board=chess.Board(fen)).get_result() is not None:
+            continue
+        rec = B.record_from_fen(fen)
+        for t in (ta, tb):
+            assert lib.hs_game_set(t, rec.ctypes.data_as(u64p), none.ctypes.data_as(u16p), 0) == 0
+        sims, seed, bits = rng.choice([24, 60, 120]), rng.randrange(1, 1000), rng.choice([5, 24])
+        for mv in range(40):
+            if lib.hs_game_result(ta) != 2:
+                finished += 1
+                break
+            ea = lib.hs_search(ta, sims, seed, bits)
+            eb = lib.hs_search_reuse(tb, sims, seed, bits)
+            assert ea >> 24 == 0 and eb >> 24 == 0
+            sa, sb = _root_stats(lib, ta), _root_stats(lib, tb)
+            assert sa == sb, (fen, mv)
+            evals_plain += ea
+            evals_reuse += eb
+            assert eb <= ea
+            # the most-visited child three times out of four (reuse pays), a random child otherwise (as the reference's
+            # unscaled Dirichlet noise often does); sometimes a move from outside the tree, which must unlink the game
+            vis = sa[3]
+            k = int(np.argmax(vis)) if rng.random() < 0.75 else rng.randrange(sa[0])
+            assert lib.hs_commit(ta, k) == lib.hs_commit(tb, k)
+            moves_played += 1
+            if rng.random() < 0.1 and lib.hs_game_result(ta) == 2:
+                out = (ctypes.c_uint16 * 256)()
+                fl = (ctypes.c_int * 2)()
+                n = lib.hs_movegen((ctypes.c_uint64 * 9)(*[int(x) for x in _cur_record(lib, ta)]), out, fl)
+                if n > 0:
+                    m = out[rng.randrange(n)]
+                    assert lib.hs_game_move(ta, m) == 1 and lib.hs_game_move(tb, m) == 1
+    assert moves_played >= 150 and finished >= 1, (moves_played, finished)
+    assert evals_reuse < 0.7 * evals_plain, (evals_reuse, evals_plain)
+
+
+def _cur_record(lib, t):
+    lib.hs_cur_record.argtypes = [ctypes.c_void_p, u64p]
+    out = (ctypes.c_uint64 * 9)()
+    lib.hs_cur_record(t, out)
+    return list(out)
