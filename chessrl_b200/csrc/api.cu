@@ -286,6 +286,8 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   A(s_moves, R * MAX_MOVES);
   A(s_nmoves, R);
   A(s_row, R);
+  A(s_path, G * 32);
+  A(s_depth, G);
   A(s_wave_n, G);
   A(g_sims_left, G);
   A(err, 1);
@@ -299,6 +301,7 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_planes, (R + 2) * 64 * 128);
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_policy, (R + 2) * CRL_N_LABELS);
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_value, R + 2);
+  if (rc == CRL_OK) rc = pool_alloc(e, &e->d_stats, 2 * (R + 2));
   if (rc == CRL_OK) rc = pool_alloc(e, &e->d_label_of, 5 * 4096);
   if (rc == CRL_OK) {
     P.eval_list = e->d_list[0];

@@ -45,6 +45,8 @@ struct crl_engine_impl {
   __nv_bfloat16* d_planes = nullptr;   // [G][64][128]
   float* d_policy = nullptr;           // [G][1968]
   float* d_value = nullptr;            // [G]
+  float* d_stats = nullptr;            // [G][2] softmax statistics (max logit, 1 / sum exp) of the rows evaluated by the network
+  PolicyView pview{};                  // how the search kernels read the last evaluation batch (set by launch_eval_batch)
   NetWeights* net = nullptr;
   bool tree_ready = false;
   int* d_list[2] = {nullptr, nullptr};   // compacted evaluation batches A (after our move) / B (leaf)
@@ -147,8 +149,10 @@ int net_create(crl_engine_impl* e);
 void net_destroy(crl_engine_impl* e);
 int net_load(crl_engine_impl* e, const float* const* w, const int64_t* sizes, int n);
 // n_dev may be null (then n_host rows); otherwise the row count is read on the device and n_host is the bound
+// view_out != null: the caller reads the policy through a PolicyView (the search kernels); where the network path allows it
+// the softmax kernel then writes only its statistics to e->d_stats and *view_out points at the logits, otherwise at `policy`
 int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, const int* n_dev, float* policy,
-                float* value, __nv_bfloat16* dbg_out = nullptr, int dbg_layer = -1);
+                float* value, __nv_bfloat16* dbg_out = nullptr, int dbg_layer = -1, PolicyView* view_out = nullptr);
 int net_debug_tower(crl_engine_impl* e, const __nv_bfloat16* planes, int n, int layer, __nv_bfloat16* act_out,
                     float* logits_out, __nv_bfloat16* pf_out, float* vf_out, float* policy, float* value);
 int net_debug_conv(crl_engine_impl* e, int layer, const __nv_bfloat16* in, int cin, int n, const __nv_bfloat16* residual,

@@ -195,6 +195,7 @@ int launch_eval_batch(crl_engine_impl* e, int which) {
     LaunchScope ls(e, KC_HASHEVAL);
     k_hash_eval_rows<<<e->cur_rows, 256, 0, e->stream>>>(e->P, which, e->eval_seed, e->eval_bits, e->d_policy, e->d_value);
     CRL_CUDA(cudaGetLastError());
+    e->pview = PolicyView{e->d_policy, CRL_N_LABELS, nullptr};
     return CRL_OK;
   }
   {
@@ -202,7 +203,7 @@ int launch_eval_batch(crl_engine_impl* e, int which) {
     k_encode_rows<<<e->cur_rows, ENC_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
     CRL_CUDA(cudaGetLastError());
   }
-  return net_forward(e, e->d_planes, e->cur_rows, e->P.eval_n, e->d_policy, e->d_value);
+  return net_forward(e, e->d_planes, e->cur_rows, e->P.eval_n, e->d_policy, e->d_value, nullptr, -1, &e->pview);
 }
 
 }  // namespace crl

@@ -1,8 +1,9 @@
 // kernels_tree.cu -- the lockstep PUCT search kernels and the game-record kernels.
 //
 // One simulation of every running game (SelfPlayTree.explore_tree, mctree.py:200-214) is the fixed kernel
-// sequence  select+expand -> [evaluate P1] -> reply -> [evaluate P2] -> finalize+backup ; games that need
-// no network evaluation in a phase (terminal leaves) simply do not enter that phase's compacted batch.
+// sequence  [backup of the previous simulation +] select+expand -> [evaluate P1] -> reply -> [evaluate P2] ; games
+// that need no network evaluation in a phase (terminal leaves) simply do not enter that phase's compacted batch.
+// simulate + backprop of a simulation run at the head of the NEXT launch of k_select_expand (k_finalize after the last).
 //   * k_select_expand : one WARP per game.  The warp walks down from the root; at every fully expanded node
 //     the 32 lanes scan the node's contiguous edge statistics (visits i32, value f64, prior f32, result i8)
 //     with coalesced loads, score them in float64 exactly as Node.get_value does, and reduce to the FIRST
@@ -224,27 +225,105 @@ __device__ __forceinline__ bool adopt_evaluation_warp(const Pools& P, int g, int
   return true;
 }
 
+// SelfPlayTree.simulate + backprop (mctree.py:259-296) of the simulation a game has in flight (exact schedule), by the
+// game's warp: the lanes cache the evaluated node's legal-order policy on its edge slots, then apply the backup to the
+// RECORDED path -- k_select_expand left the edge index of depth d in s_path[g][d] -- one lane per level: the
+// (visits += 1, value += v) updates of different edges are independent, so up to 32 levels cost one round of memory
+// latency instead of a parent-pointer chase of three dependent loads per level.  Deeper paths fall back to the chase.
+__device__ __forceinline__ void finalize_pending(const Pools& P, int g, int lane, const PolicyView& pv,
+                                                 const float* __restrict__ value, const int16_t* __restrict__ label_of) {
+  const int kind = P.s_kind[g];
+  if (kind == KIND_IDLE || kind == KIND_NEED_REPLY) return;   // nothing in flight (NEED_REPLY: a row the evaluator never saw)
+  const int node = P.s_node[g];
+  NodeRec& n = P.nodes[(long long)g * P.NN + node];
+  double v;
+  if (kind == KIND_EVAL_LEAF) {
+    const int row = P.s_row[g];
+    const long long ebase = (long long)g * P.EA + n.edge0;
+    const int L = n.n_legal;
+    for (int i = lane; i < L; i += 32) {     // store_priors, mirrored: legal move i -> child slot L-1-i
+      const u16 m = P.e_move[ebase + i];
+      P.e_prior[ebase + (L - 1 - i)] = policy_at(pv, row, label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]);
+    }
+    const float vf = value[row];
+    v = (double)vf;                                           // float(v) of a float32 (predict_worker.py:111)
+    if (lane == 0) {
+      n.v = vf;                                               // kept for the next move's search (evaluation reuse)
+      n.evald = 1;
+      atomicAdd((unsigned long long*)&P.counters[1], 1ull);   // the evaluation of this leaf
+    }
+  } else if (kind == KIND_EVAL_REUSED) {
+    v = (double)n.v;                                          // the same float32 the previous search got from the network
+  } else {
+    v = (double)n.result;                                     // terminal: Game.get_result (mctree.py:268)
+  }
+  const int depth = P.s_depth[g];
+  if (depth >= 0) {
+    if (lane < depth) {
+      const long long e = (long long)g * P.EA + P.s_path[(long long)g * 32 + lane];
+      P.e_visits[e] += 1;
+      P.e_value[e] += v;
+    }
+    if (lane == 0) {
+      P.r_visits[g] += 1;
+      P.r_value[g] += v;
+    }
+  } else if (lane == 0) {
+    backup(P, g, node, v);
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&P.counters[0], 1ull);
+    P.s_kind[g] = KIND_IDLE;
+  }
+  __syncwarp();                                               // the select that follows reads these statistics
+}
+
+// The head of one lockstep simulation: finish the simulation the game still has in flight (its evaluation batch B ran
+// after the previous launch of this kernel), then select + expand the next one.  Fusing the two removes a launch and its
+// tail from every simulation and lets the backup run level-parallel on the recorded path.
 // (7 blocks = 28 warps per SM: 148 x 28 = 4,144 resident warps, so 4,096 games run as ONE wave instead of 1.5)
 // list_b / n_b: batch B of this simulation (node states to evaluate), which k_reply fills; with evaluation reuse a warp
 // whose new child has a twin in the previous tree plays the twin's reply at once -- no batch-A row -- and normally takes
 // the twin's value and priors as well, so that simulation runs without the network.
-__global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, int* list_b, int* n_b) {
+__global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, PolicyView pv, const float* __restrict__ value,
+                                                              const int16_t* __restrict__ label_of, int* list_b, int* n_b) {
   __shared__ u16 s_gen[TREE_WARPS][MAX_MOVES];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (g >= P.G) return;
-  if (!game_running(P, g)) {
-    if (lane == 0) P.s_kind[g] = KIND_IDLE;
-    return;
+  finalize_pending(P, g, lane, pv, value, label_of);
+  if (!game_running(P, g)) return;             // s_kind[g] is KIND_IDLE
+  // SelfPlayTree.select (mctree.py:216-229), recording the edge taken at every level
+  int node = 0, depth = 0, my_edge = 0, term = 0;
+  const WarpScan<false> scan{P, g, lane};
+  for (;;) {
+    const NodeRec& n = P.nodes[(long long)g * P.NN + node];
+    if (n.result != RESULT_NONE) {
+      term = 1;
+      break;
+    }
+    if (n.n_exp < n.n_legal) break;
+    const int e = n.edge0 + scan(n);
+    if (lane == (depth & 31)) my_edge = e;
+    ++depth;
+    node = P.e_child[(long long)g * P.EA + e];
   }
-  int node, term;
-  select_descend(P, g, WarpScan<false>{P, g, lane}, &node, &term);
   if (term) {
+    if (depth <= 32) P.s_path[(long long)g * 32 + lane] = my_edge;
     if (lane == 0) {
+      P.s_depth[g] = depth <= 32 ? depth : -1;
       P.s_node[g] = node;
       P.s_kind[g] = KIND_TERMINAL;
     }
     return;
+  }
+  {
+    const NodeRec& pn = P.nodes[(long long)g * P.NN + node];
+    const int e = pn.edge0 + pn.n_exp;         // the edge the new child is about to take
+    if (lane == (depth & 31)) my_edge = e;
+    ++depth;
+    if (depth <= 32) P.s_path[(long long)g * 32 + lane] = my_edge;
+    if (lane == 0) P.s_depth[g] = depth <= 32 ? depth : -1;
   }
   int child, twin;
   int kind = expand_child_warp(P, g, g, node, lane, &child, &twin);
@@ -337,8 +416,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_wave(Pools P) {
 }
 
 // simulate + backprop of the wave, in slot order (value += v is a float64 sum: the order is part of the result)
-__global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const float* __restrict__ policy,
-                                                              const float* __restrict__ value,
+__global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, PolicyView pv, const float* __restrict__ value,
                                                               const int16_t* __restrict__ label_of) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -354,12 +432,11 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const flo
     double v;
     if (kind == KIND_EVAL_LEAF) {
       const int row = P.s_row[slot];
-      const float* prow = policy + (long long)row * CRL_N_LABELS;
       const long long ebase = (long long)g * P.EA + n.edge0;
       const int L = n.n_legal;
       for (int i = lane; i < L; i += 32) {
         const u16 m = P.e_move[ebase + i];
-        P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+        P.e_prior[ebase + (L - 1 - i)] = policy_at(pv, row, label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]);
       }
       const float vf = value[row];
       v = (double)vf;
@@ -373,6 +450,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_finalize_wave(Pools P, const flo
     if (lane == 0) {
       backup(P, g, node, v);
       vloss_add(P, g, node, -1);
+      P.s_kind[slot] = KIND_IDLE;             // nothing in flight any more (k_select_expand finishes what it finds)
     }
   }
   if (lane == 0 && used > 0) atomicAdd((unsigned long long*)&P.counters[0], (unsigned long long)used);
@@ -390,9 +468,8 @@ __global__ void __launch_bounds__(256) k_wave_left(Pools P, int* out) {
 // rows of batch A (positions after our move) -> opponent reply, node state, batch B.
 // One WARP per row: the lanes gather the legal-masked policy in parallel and reduce to the FIRST maximum
 // (agentdistributed.py:56-58), then play the reply and build the node together (mctree.py:245-249).
-__global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, const float* __restrict__ policy,
-                                                      const int16_t* __restrict__ label_of, int* list_b,
-                                                      int* n_b) {
+__global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, PolicyView pv, const int16_t* __restrict__ label_of,
+                                                      int* list_b, int* n_b) {
   __shared__ u16 s_gen[TREE_WARPS][MAX_MOVES];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -402,14 +479,13 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, const float* _
   const int slot = P.eval_list[r];
   const int g = slot / P.K;
   const int child = P.s_node[slot];
-  const float* row = policy + (long long)r * CRL_N_LABELS;
   const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
   const int n1 = P.s_nmoves[slot];
   float best_p = -CUDART_INF_F;
   int best_i = 0x7fffffff;
   for (int i = lane; i < n1; i += 32) {
     const u16 m = moves1[i];
-    const float p = row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    const float p = policy_at(pv, r, label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]);
     if (p > best_p) {
       best_p = p;
       best_i = i;
@@ -434,43 +510,13 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, const float* _
   }
 }
 
-// SelfPlayTree.simulate + backprop (mctree.py:259-296) for every running game; one WARP per game: the lanes cache
-// the evaluated node's legal-order policy on its edge slots in parallel, lane 0 walks the backup path.
-__global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, const float* __restrict__ policy,
-                                                         const float* __restrict__ value,
+// the last simulation of a crl_mcts_simulate call has no following k_select_expand to finish it: this does
+__global__ void __launch_bounds__(TREE_BLOCK) k_finalize(Pools P, PolicyView pv, const float* __restrict__ value,
                                                          const int16_t* __restrict__ label_of) {
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (g == 0 && lane == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)*P.eval_n);
   if (g >= P.G) return;
-  if (!game_running(P, g) || P.s_kind[g] == KIND_IDLE) return;
-  const int node = P.s_node[g];
-  const int kind = P.s_kind[g];
-  NodeRec& n = P.nodes[(long long)g * P.NN + node];
-  double v;
-  if (kind == KIND_EVAL_LEAF) {
-    const int row = P.s_row[g];
-    const float* prow = policy + (long long)row * CRL_N_LABELS;
-    const long long ebase = (long long)g * P.EA + n.edge0;
-    const int L = n.n_legal;
-    for (int i = lane; i < L; i += 32) {     // store_priors, mirrored: legal move i -> child slot L-1-i
-      const u16 m = P.e_move[ebase + i];
-      P.e_prior[ebase + (L - 1 - i)] = prow[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
-    }
-    const float vf = value[row];
-    v = (double)vf;                                           // float(v) of a float32 (predict_worker.py:111)
-    if (lane == 0) {
-      n.v = vf;                                               // kept for the next move's search (evaluation reuse)
-      n.evald = 1;
-    }
-  } else if (kind == KIND_EVAL_REUSED) {
-    v = (double)n.v;                                          // the same float32 the previous search got from the network
-  } else {
-    v = (double)n.result;                                     // terminal: Game.get_result (mctree.py:268)
-  }
-  if (lane != 0) return;
-  atomicAdd((unsigned long long*)&P.counters[0], 1ull);
-  backup(P, g, node, v);
+  finalize_pending(P, g, lane, pv, value, label_of);
 }
 
 // Tree(root): build node 0 of every running game and queue it for evaluation
@@ -492,18 +538,18 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __r
   P.s_row[g] = row;
 }
 
-__global__ void __launch_bounds__(TREE_BLOCK) k_root_priors(Pools P, const float* __restrict__ policy,
+__global__ void __launch_bounds__(TREE_BLOCK) k_root_priors(Pools P, PolicyView pv,
                                                             const int16_t* __restrict__ label_of) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = *P.eval_n;
   if (r == 0) atomicAdd((unsigned long long*)&P.counters[1], (unsigned long long)n);
   if (r >= n) return;
   const int g = P.eval_list[r];
-  store_priors(P, g, 0, policy + (long long)r * CRL_N_LABELS, label_of);
+  store_priors_of(P, g, 0, [&](int label) { return policy_at(pv, r, label); }, label_of);
 }
 
 // AgentDistributed.best_move(real_game=True): argmax of the legal-masked policy of the current position
-__global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, const float* __restrict__ policy,
+__global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, PolicyView pv,
                                                             const int16_t* __restrict__ label_of,
                                                             u16* __restrict__ picks) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,7 +558,8 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_policy_move(Pools P, const float
   const NodeRec& root = P.nodes[(long long)g * P.NN];
   const u16* moves = P.e_move + (long long)g * P.EA + root.edge0;
   u16 mv = MOVE_NONE;
-  if (root.n_legal > 0) mv = moves[argmax_legal(policy + (long long)r * CRL_N_LABELS, label_of, moves, root.n_legal)];
+  if (root.n_legal > 0)
+    mv = moves[argmax_legal_of([&](int label) { return policy_at(pv, r, label); }, label_of, moves, root.n_legal)];
   picks[g] = mv;
   game_move(P, g, mv);
   P.g_prev_root[g] = -1;
@@ -679,7 +726,7 @@ int tree_begin_move(crl_engine_impl* e, const u8* mask_dev, bool use_prev) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_root_priors<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of);
+    k_root_priors<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_label_of);
     CRL_CUDA(cudaGetLastError());
   }
   return CRL_OK;
@@ -694,26 +741,28 @@ static int one_simulation(crl_engine_impl* e) {
   e->cur_rows = e->G;
   {
     LaunchScope ls(e, KC_TREE);
-    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_list[1], e->d_n + 1);
+    k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(
+        e->P, e->pview, e->d_value, e->d_label_of, e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   int rc = launch_eval_batch(e, 1);
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+    k_reply<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_label_of,
                                                                                    e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
   use_list(e, 1);
-  rc = launch_eval_batch(e, 2);
-  if (rc != CRL_OK) return rc;
-  {
-    LaunchScope ls(e, KC_TREE);
-    k_finalize<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
-                                                                                      e->d_label_of);
-    CRL_CUDA(cudaGetLastError());
-  }
+  return launch_eval_batch(e, 2);      // its results are consumed by the next k_select_expand, or by finish_simulations
+}
+
+// simulate + backprop of the last simulation in flight (exact schedule)
+static int finish_simulations(crl_engine_impl* e) {
+  e->P.K = 1;
+  LaunchScope ls(e, KC_TREE);
+  k_finalize<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_value, e->d_label_of);
+  CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }
 
@@ -733,7 +782,7 @@ static int one_wave(crl_engine_impl* e, int K) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_reply<<<div_up((long long)e->cur_rows * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of,
+    k_reply<<<div_up((long long)e->cur_rows * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_label_of,
                                                                                          e->d_list[1], e->d_n + 1);
     CRL_CUDA(cudaGetLastError());
   }
@@ -742,7 +791,7 @@ static int one_wave(crl_engine_impl* e, int K) {
   if (rc != CRL_OK) return rc;
   {
     LaunchScope ls(e, KC_TREE);
-    k_finalize_wave<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_value,
+    k_finalize_wave<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_value,
                                                                                            e->d_label_of);
     CRL_CUDA(cudaGetLastError());
   }
@@ -783,7 +832,7 @@ int tree_simulate(crl_engine_impl* e, int n_sims, int K) {
   for (;;) {
     int rc = tree_run_steps(e, n_steps, K);
     if (rc != CRL_OK) return rc;
-    if (K <= 1) return CRL_OK;
+    if (K <= 1) return finish_simulations(e);
     int left = 0;
     rc = wave_left(e, &left);
     if (rc != CRL_OK) return rc;
@@ -848,7 +897,7 @@ int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev) {
   int rc = tree_begin_move(e, mask_dev, false);   // root_init + evaluation of the current positions
   if (rc != CRL_OK) return rc;
   LaunchScope ls(e, KC_TREE);
-  k_policy_move<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->d_policy, e->d_label_of, picks_dev);
+  k_policy_move<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_label_of, picks_dev);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

@@ -1308,6 +1308,7 @@ struct TailParams {
   const float* bv2;      // [1]
   float* policy;         // [rows][1968]
   float* value;          // [rows]
+  float* stats;          // null, or [rows][2]: write (max logit, 1 / sum exp) INSTEAD of the probability row
 };
 __global__ void __launch_bounds__(256) k_softmax_value(TailParams p) {
   __shared__ float s_vf[8][64];
@@ -1359,11 +1360,20 @@ __global__ void __launch_bounds__(256) k_softmax_value(TailParams p) {
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   const float inv = 1.0f / s;
-  float* out = p.policy + (long long)pos * CRL_N_LABELS;
+  if (p.stats) {
+    // the search reads ~35 of the 1,968 probabilities of a row: hand it (max, 1 / sum) and let it evaluate
+    // expf(logit - max) * inv -- this kernel's own expression -- for the entries it needs (PolicyView, tree_core.cuh)
+    if (lane == 0) {
+      p.stats[2 * pos] = m;
+      p.stats[2 * pos + 1] = inv;
+    }
+  } else {
+    float* out = p.policy + (long long)pos * CRL_N_LABELS;
 #pragma unroll
-  for (int k = 0; k < 62; ++k) {
-    const int j = lane + 32 * k;
-    if (j < CRL_N_LABELS) out[j] = x[k] * inv;
+    for (int k = 0; k < 62; ++k) {
+      const int j = lane + 32 * k;
+      if (j < CRL_N_LABELS) out[j] = x[k] * inv;
+    }
   }
   float v = 0.f;
   for (int j = lane; j < 256; j += 32) v = fmaf(s_hid[warp][j], p.wv2[j], v);
@@ -1787,7 +1797,8 @@ static int launch_conv_v2(crl_engine_impl* e, const CUtensorMap& map_in, int L, 
 }
 
 // policy dense layer (128 -> 1968, zero padded to 2048) as a tcgen05 GEMM, then softmax + value head
-static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, float* policy, float* value) {
+static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, float* policy, float* value,
+                           PolicyView* view_out) {
   NetWeights* nw = e->net;
   ConvParams2 p;
   memset(&p, 0, sizeof(p));
@@ -1821,6 +1832,16 @@ static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, flo
   t.bv2 = nw->bv2;
   t.policy = policy;
   t.value = value;
+  t.stats = nullptr;
+  if (view_out) {
+    static const bool full = []() { const char* f = getenv("CRL_FULL_SOFTMAX"); return f && f[0] == '1'; }();
+    if (full) {
+      *view_out = PolicyView{policy, CRL_N_LABELS, nullptr};
+    } else {
+      t.stats = e->d_stats;
+      *view_out = PolicyView{nw->logits, 2048, e->d_stats};
+    }
+  }
   LaunchScope ls(e, KC_HEADS);
   k_softmax_value<<<div_up(n_host, 8), 256, 0, e->stream>>>(t);
   CRL_CUDA(cudaGetLastError());
@@ -1828,7 +1849,8 @@ static int launch_heads_v2(crl_engine_impl* e, const int* n_dev, int n_host, flo
 }
 
 int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, const int* n_dev, float* policy,
-                float* value, __nv_bfloat16* dbg_out, int dbg_layer) {
+                float* value, __nv_bfloat16* dbg_out, int dbg_layer, PolicyView* view_out) {
+  if (view_out) *view_out = PolicyView{policy, CRL_N_LABELS, nullptr};   // unless the heads below switch to statistics
   NetWeights* nw = e->net;
   if (!nw || !nw->loaded) {
     set_error("network weights are not loaded (crl_net_load_host)");
@@ -1881,7 +1903,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
         k_trunk<<<2 * pairs, CONV_THREADS, V2_SMEM_BYTES, e->stream>>>(nw->map_planes, nw->d_maps, nw->d_layers, tp);
       CRL_CUDA(cudaGetLastError());
     }
-    return launch_heads_v2(e, n_dev, n_host, policy, value);
+    return launch_heads_v2(e, n_dev, n_host, policy, value, view_out);
   }
   if (nw->use_v2) {
     if ((rc = launch_conv_v2(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0, false))) return rc;
@@ -1891,7 +1913,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
       if ((rc = launch_conv_v2(e, nw->map_act[1], 2 + 2 * b, n_dev, n_host, nw->act[0], last ? nullptr : nw->act[0], 1, last)))
         return rc;
     }
-    return launch_heads_v2(e, n_dev, n_host, policy, value);
+    return launch_heads_v2(e, n_dev, n_host, policy, value, view_out);
   }
   // stem: conv only (model.py:33-34 -- no BatchNorm / activation after it)
   if ((rc = launch_conv(e, nw->map_planes, 0, n_dev, n_host, nullptr, nw->act[0], 0))) return rc;

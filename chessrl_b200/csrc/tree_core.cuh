@@ -85,6 +85,8 @@ struct Pools {
   u16* s_moves;     // [G*K][MAX_MOVES] legal moves of the position awaiting its reply
   int* s_nmoves;    // [G*K]
   int* s_row;       // [G*K] row of this slot in the current evaluation batch
+  int* s_path;      // [G][32] exact schedule: edge (index inside the game's arena) taken at every level of the select
+  int* s_depth;     // [G] levels recorded in s_path, -1 = deeper than 32 (the backup then chases parent pointers)
   int* s_wave_n;    // [G] slots used by the current wave
   int* g_sims_left; // [G] simulations of the current crl_mcts_simulate call still to run (wave mode)
   int* eval_list;   // [G*K] slot of every batch row
@@ -92,6 +94,26 @@ struct Pools {
   int* err;         // [1] ERR_* flags
   long long* counters;  // [0] simulations [1] evaluations run [2] evaluations taken from the previous tree instead
 };
+
+// The evaluator's policy output as the search kernels read it.  stats == null: base[row][label] IS the probability
+// (hash evaluator, crl_net_forward).  stats != null (network inside the search): base holds the policy LOGITS and
+// stats[row] = (max logit, 1 / sum exp) -- the softmax kernel then writes 8 bytes per row instead of the 7.9 KB
+// probability row of which the search reads ~35 entries; expf(x - max) * inv is the very expression k_softmax_value
+// evaluates for a full row, so both views give the same bits.
+struct PolicyView {
+  const float* base;
+  int ld;
+  const float* stats;
+};
+CRL_HD float policy_at(const PolicyView& pv, int row, int label) {
+  const float x = pv.base[(long long)row * pv.ld + label];
+  if (!pv.stats) return x;
+#if defined(__CUDA_ARCH__)
+  return expf(x - pv.stats[2 * row]) * pv.stats[2 * row + 1];
+#else
+  return __builtin_expf(x - pv.stats[2 * row]) * pv.stats[2 * row + 1];
+#endif
+}
 
 CRL_HD Board load_soa(const u64* base, long long stride, long long i) {
   Board b;
@@ -377,18 +399,27 @@ CRL_HD int expand_child(const Pools& P, int g, int slot, int parent, int* out_ch
 }
 
 // first maximum of the legal-masked policy (agentdistributed.py:56-58, 80-82)
-CRL_HD int argmax_legal(const float* policy_row, const int16_t* label_of, const u16* moves, int n) {
+// `row(label)` = probability of a label in the evaluated row
+template <class Row>
+CRL_HD int argmax_legal_of(Row row, const int16_t* label_of, const u16* moves, int n) {
   int best = 0;
   float best_p = 0.f;
   for (int i = 0; i < n; ++i) {
     u16 m = moves[i];
-    float p = policy_row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    float p = row((int)label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]);
     if (i == 0 || p > best_p) {
       best_p = p;
       best = i;
     }
   }
   return best;
+}
+struct PlainRow {
+  const float* p;
+  CRL_HD float operator()(int label) const { return p[label]; }
+};
+CRL_HD int argmax_legal(const float* policy_row, const int16_t* label_of, const u16* moves, int n) {
+  return argmax_legal_of(PlainRow{policy_row}, label_of, moves, n);
 }
 
 // SelfPlayTree.expand, second half (mctree.py:245-249): the opponent answers with its policy argmax, the
@@ -456,15 +487,18 @@ CRL_HD int wave_take_slot(const Pools& P, int g, int slot, int what, int node) {
 }
 
 // cache the legal-order policy of an evaluated node on its edge slots (what _update_prior will hand out)
-CRL_HD void store_priors(const Pools& P, int g, int node, const float* policy_row, const int16_t* label_of) {
+template <class Row>
+CRL_HD void store_priors_of(const Pools& P, int g, int node, Row row, const int16_t* label_of) {
   const NodeRec& n = P.nodes[(long long)g * P.NN + node];
   long long ebase = (long long)g * P.EA + n.edge0;
   for (int i = 0; i < n.n_legal; ++i) {
     u16 m = P.e_move[ebase + i];
     // mirror index: legal move i is expanded as child (n_legal-1-i), whose prior slot is (n_legal-1-i)
-    P.e_prior[ebase + (n.n_legal - 1 - i)] =
-        policy_row[label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]];
+    P.e_prior[ebase + (n.n_legal - 1 - i)] = row((int)label_of[(int)mv_promo(m) * 4096 + mv_from(m) * 64 + mv_to(m)]);
   }
+}
+CRL_HD void store_priors(const Pools& P, int g, int node, const float* policy_row, const int16_t* label_of) {
+  store_priors_of(P, g, node, PlainRow{policy_row}, label_of);
 }
 
 // SelfPlayTree.backprop (mctree.py:278-296): visits += 1, value += v from the leaf to the root

@@ -160,6 +160,8 @@ void* hs_tree_new(int NN, int EA, const int16_t* label_of) {
   P.s_moves = (u16*)calloc(HS_KMAX * MAX_MOVES, 2);
   P.s_nmoves = (int*)calloc(HS_KMAX, 4);
   P.s_row = (int*)calloc(HS_KMAX, 4);
+  P.s_path = nullptr;      // device-only (level-parallel backup)
+  P.s_depth = nullptr;
   P.s_wave_n = (int*)calloc(1, 4);
   P.g_sims_left = (int*)calloc(1, 4);
   P.eval_list = (int*)calloc(HS_KMAX, 4);
