@@ -28,6 +28,7 @@ struct EncShared {
 // six black piece bits, "no white piece", six white piece bits; bit 126 = side to move).  Step 2: all threads expand
 // mask bytes to bf16 and store 16 bytes each, 2 KB contiguous per block-wide store -- the kernel is then bound by the
 // 16 KB it writes per position, not by bit fiddling.
+template <int T>
 __device__ __forceinline__ void write_planes(const EncShared& s, unsigned (*s_mask)[4],
                                              __nv_bfloat16* __restrict__ out) {
   if (threadIdx.x < 64) {
@@ -57,8 +58,8 @@ __device__ __forceinline__ void write_planes(const EncShared& s, unsigned (*s_ma
   __syncthreads();
   uint4* dst = reinterpret_cast<uint4*>(out);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int id = j * ENC_THREADS + threadIdx.x;   // 16-byte chunk id: 64 squares x 16 chunks of 8 channels
+  for (int j = 0; j < 1024 / T; ++j) {
+    const int id = j * T + threadIdx.x;             // 16-byte chunk id: 64 squares x 16 chunks of 8 channels
     const int cell = id >> 4, chunk = id & 15;
     const unsigned bits = (s_mask[cell][chunk >> 2] >> ((chunk & 3) * 8)) & 0xFFu;
     uint4 q;
@@ -91,12 +92,14 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_boards(const u64* __rest
     }
   }
   __syncthreads();
-  write_planes(s, s_mask, planes + (long long)i * 64 * 128);
+  write_planes<ENC_THREADS>(s, s_mask, planes + (long long)i * 64 * 128);
 }
 
 // tree / game batches: row r -> slot eval_list[r] (game = slot / K); position = (s_node[slot], which) or the root
-// when which==0
-__global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
+// when which==0.  64 threads per row: the history walk is a short pointer chase by one thread, and with 32 resident
+// blocks per SM a whole 4,096-row batch is one wave, so every chase overlaps the other rows' stores.
+static constexpr int ENC_ROW_THREADS = 64;
+__global__ void __launch_bounds__(ENC_ROW_THREADS) k_encode_rows(Pools P, int which,
                                                              __nv_bfloat16* __restrict__ planes) {
   __shared__ EncShared s;
   __shared__ unsigned s_mask[64][4];
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(ENC_THREADS) k_encode_rows(Pools P, int which,
     s.turn = (int)(meta & 1);
   }
   __syncthreads();
-  write_planes(s, s_mask, planes + (long long)r * 64 * 128);
+  write_planes<ENC_ROW_THREADS>(s, s_mask, planes + (long long)r * 64 * 128);
 }
 
 __global__ void k_policy_index(const u16* __restrict__ moves, const int* __restrict__ counts, int n,
@@ -200,7 +203,7 @@ int launch_eval_batch(crl_engine_impl* e, int which) {
   }
   {
     LaunchScope ls(e, KC_ENCODE);
-    k_encode_rows<<<e->cur_rows, ENC_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
+    k_encode_rows<<<e->cur_rows, ENC_ROW_THREADS, 0, e->stream>>>(e->P, which, e->d_planes);
     CRL_CUDA(cudaGetLastError());
   }
   return net_forward(e, e->d_planes, e->cur_rows, e->P.eval_n, e->d_policy, e->d_value, nullptr, -1, &e->pview);

@@ -104,7 +104,7 @@ __device__ __forceinline__ int analyse_position_warp(const Pools& P, int g, cons
 // expand_child (tree_core.cuh; mctree.py:241-244) run by the whole warp: uniform reads and arithmetic in every lane,
 // the node's fields written by lane 0, the legal moves of P1 generated cooperatively into the slot's move row.
 __device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot, int parent, int lane, int* out_child,
-                                                 int* out_twin = nullptr) {
+                                                 int* out_twin = nullptr, int* out_n_moves = nullptr) {
   NodeRec& pn = P.nodes[(long long)g * P.NN + parent];
   const int child = P.g_nnodes[g];
   const int k = pn.n_exp;
@@ -148,6 +148,7 @@ __device__ __forceinline__ int expand_child_warp(const Pools& P, int g, int slot
   u64 key;
   const int res = analyse_position_warp(P, g, b, at, P.s_moves + (long long)slot * MAX_MOVES, lane, &n_moves, &key);
   *out_child = child;
+  if (out_n_moves) *out_n_moves = n_moves;
   if (lane == 0) {
     cn.key1 = key;
     P.s_nmoves[slot] = n_moves;
@@ -325,12 +326,12 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
     if (depth <= 32) P.s_path[(long long)g * 32 + lane] = my_edge;
     if (lane == 0) P.s_depth[g] = depth <= 32 ? depth : -1;
   }
-  int child, twin;
-  int kind = expand_child_warp(P, g, g, node, lane, &child, &twin);
+  int child, twin, n1;
+  int kind = expand_child_warp(P, g, g, node, lane, &child, &twin, &n1);
   if (kind == KIND_NEED_REPLY && twin >= 0) {
     const u16 reply = P.nodes_prev[(long long)g * P.NN + twin].reply;
     const u16* moves1 = P.s_moves + (long long)g * MAX_MOVES;
-    const int n1 = P.s_nmoves[g];
+    __syncwarp();                                  // the move row was written by all lanes of this warp just now
     int pick = 0x7fffffff;
     for (int i = lane; i < n1; i += 32)
       if (moves1[i] == reply) pick = i;
@@ -524,10 +525,12 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __r
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= P.G) return;
   P.s_kind[g] = KIND_IDLE;
-  if (!game_running(P, g) || (mask && !mask[g])) {
-    if (use_prev) P.g_prev_root[g] = -1;
+  if (!game_running(P, g)) {
+    P.g_nnodes[g] = 0;          // no tree this move: root statistics of a finished / parked lane read as empty, not as
+    P.g_prev_root[g] = -1;      // whatever an earlier search left in this pool
     return;
   }
+  if (mask && !mask[g]) return;
   P.s_node[g] = 0;
   if (!root_init(P, g, use_prev != 0)) {       // priors taken over from the previous tree: no evaluation
     atomicAdd((unsigned long long*)&P.counters[2], 1ull);

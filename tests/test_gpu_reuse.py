@@ -31,8 +31,9 @@ def _play(engine, lanes, sims, n_moves, reuse, noise, seed, refill=True, picker=
         engine.mcts_begin_move()
         engine.mcts_simulate(sims, 1)
         st = engine.root_stats(want=WANT)
-        trace.append({k: st[k][:lanes].copy() for k in st})
         live = (sp._results == B.RESULT_NONE) & ~sp._retired
+        assert (st["n_children"][:lanes][~live] == 0).all()      # a lane without a running game has no tree this move
+        trace.append({k: st[k][:lanes].copy() for k in st})
         picks = np.full(engine.max_games, -1, dtype=np.int32)
         if picker is None:
             picks[:lanes] = pick_moves(st["visits"][:lanes], st["n_children"][:lanes], st["root_visits"][:lanes],
@@ -102,6 +103,7 @@ def test_reuse_follows_the_most_visited_child_and_survives_foreign_moves():
             e.mcts_begin_move()
             e.mcts_simulate(100, 1)
             st = e.root_stats(want=WANT)
+            assert (st["n_children"][~sp.running()] == 0).all()  # a finished game has no tree this move
             trace.append({k: st[k].copy() for k in st})
             e.commit(picker(mv, st, sp.running()), apply=True)
             sp._read_status()
