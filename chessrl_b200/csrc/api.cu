@@ -241,6 +241,8 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   {
     const char* g = getenv("CRL_NO_GRAPH");
     e->use_graph = !(g && g[0] == '1');
+    const char* pd = getenv("CRL_NO_PDL");
+    e->perft_pdl = !(pd && pd[0] == '1');
     const char* pp = getenv("CRL_PERFT_PAIR");
     e->perft_pair = !pp ? 0 : pp[0] == '5' ? 5 : pp[0] == '6' ? 6 : 0;
   }
@@ -393,7 +395,7 @@ int crl_perft_root_shard_host(crl_engine* e, const uint64_t* root_host, int dept
                               int n_shards, int64_t shard_min_frontier, uint64_t* total_host, int64_t* lanes_host,
                               int32_t* bfs_plies_host) {
   CHECK_ENGINE(e);
-  if (shard_min_frontier < 128) shard_min_frontier = 128;     // the first kernel's tiny plies are never split
+  if (shard_min_frontier < 256) shard_min_frontier = 256;     // the first kernel's plies (<= 218 boards in) are never split
   if (!root_host || !total_host || depth < 0 || min_frontier < 1 || n_shards < 1 || shard < 0 || shard >= n_shards) {
     set_error("crl_perft_root_host: bad arguments");
     return CRL_EINVAL;

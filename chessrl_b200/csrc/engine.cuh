@@ -60,6 +60,7 @@ struct crl_engine_impl {
   int perft_pair = 0;                    // 0: expand the last-but-one ply into HBM, then walk it (default: measured
                                          // faster); CRL_PERFT_PAIR=5 / 6: the last two plies in one pass (k_perft_pair,
                                          // 96- / 80-register build)
+  bool perft_pdl = true;                 // plies launched as programmatic dependent launches (CRL_NO_PDL=1: plain launches)
   // pinned staging
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;

@@ -10,6 +10,30 @@ namespace crl {
 
 static constexpr int RULES_BLOCK = 128;
 
+// Programmatic dependent launch (sm_90+): the plies of crl_perft_root_host form a chain of short kernels, each reading
+// the control block the previous one wrote.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization a kernel is
+// set up while its predecessor still runs and blocks here until that one has completed and flushed its memory --
+// the launch latency between the plies overlaps instead of adding up.  A no-op for a normal launch.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// "my dependents may be set up now": once every block of this grid has said so (or exited), the next ply's blocks are
+// scheduled into free slots and sit in grid_dependency_wait() until this grid is complete
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- movegen: boards -> move lists -------------------------------------------------------------------
 // Moves are generated straight into a shared-memory row per board (rows of 33 words: lanes writing their k-th move hit
 // 32 different banks) and copied out by QUADS of lanes -- 4 lanes x 8 bytes = one 32-byte sector of a board's row per
@@ -396,6 +420,8 @@ __global__ void __launch_bounds__(RULES_BLOCK) k_bfs_ply(u64* __restrict__ buf0,
   __shared__ u64 s_board[RULES_BLOCK / 32][9][32];
   __shared__ __align__(8) u16 s_moves[RULES_BLOCK / 32][32][BFS_CAP];
   __shared__ int s_pre[RULES_BLOCK / 32][33];
+  grid_launch_dependents();
+  grid_dependency_wait();                                              // launched early (programmatic dependent launch)
   if (!bfs_active(ctl, min_frontier, depth, pair)) return;            // uniform for the whole grid: nobody commits before
   const long long n = (long long)ctl[0];                              // every block has read the control block
   const int plies = (int)ctl[2];
@@ -426,12 +452,14 @@ struct RootRecord {
   u64 w[9];
 };
 static constexpr int FIRST_THREADS = 512;          // 16 warps: the 20 children of the start position in two rounds
-static constexpr long long FIRST_MAX = 96;         // k_bfs_first keeps going while the frontier is at most this large
+static constexpr long long FIRST_MAX = 256;        // k_bfs_first runs its (at most two) plies whatever the root's move count
+                                                   // (<= 218), so the host knows which plies are left for the grid kernels
 __global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u64* __restrict__ buf0, u64* __restrict__ buf1,
                                                              long long cap, unsigned long long* __restrict__ ctl,
                                                              long long min_frontier, int depth, int pair, int n_plies,
                                                              ShardSpec sh) {
   __shared__ u16 s_gen[FIRST_THREADS / 32][MAX_MOVES];
+  grid_launch_dependents();
   if (threadIdx.x < CTL_WORDS) ctl[threadIdx.x] = threadIdx.x == 0 ? 1ull : 0ull;
   if (threadIdx.x < 9) buf0[(long long)threadIdx.x * cap] = root.w[threadIdx.x];     // column 0 of the SoA buffer
   __syncthreads();
@@ -453,6 +481,7 @@ __global__ void __launch_bounds__(FIRST_THREADS) k_bfs_first(RootRecord root, u6
 __global__ void __launch_bounds__(RULES_BLOCK) k_perft_walk(const u64* __restrict__ buf0, const u64* __restrict__ buf1,
                                                             long long cap, unsigned long long* __restrict__ ctl, int depth,
                                                             int bulk, int pair, ShardSpec sh) {
+  grid_dependency_wait();
   if (ctl[3]) return;
   const long long n = (long long)ctl[0];
   const bool split_here = sh.n_shards > 1 && !ctl[9];     // the frontier never grew to shard_min boards: split it now
@@ -656,8 +685,8 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
   if (depth < 2) pair = 0;
   const int max_plies = depth - 1 - (pair ? 1 : 0) > 0 ? depth - 1 - (pair ? 1 : 0) : 0;
   const int max_grid = 148 * 12;
-  // the first kernel always expands the root (ply 1) and goes on while the frontier stays tiny; ply 2 is enqueued as a
-  // grid ply as well (a no-op if the first kernel already did it -- it cannot be known here) so no ply is ever skipped
+  // the first kernel expands the root and its children (plies 1 and 2: at most 218 boards go in); the grid kernels take
+  // the plies after that -- no launch that turns out to be a no-op (it cost 3 us + a launch gap per call)
   const int first_plies = max_plies < 2 ? max_plies : 2;
   RootRecord rr;
   for (int k = 0; k < 9; ++k) rr.w[k] = root[k];
@@ -666,13 +695,18 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
     k_bfs_first<<<1, FIRST_THREADS, 0, e->stream>>>(rr, buf0, buf1, cap, ctl, min_frontier, depth, pair, first_plies, sh);
     CRL_CUDA(cudaGetLastError());
   }
-  // How many boards a ply holds is only known on the device (and whether the first kernel ran one ply or two), so
-  // every grid ply gets the full grid: blocks without work leave after reading the control block.
-  long long bound = 218 < cap ? 218 : cap;
-  for (int ply = 1; ply < max_plies; ++ply) {
+  // How many boards a ply holds is only known on the device, so every grid ply gets the full grid: blocks without
+  // work leave after reading the control block.
+  long long bound = 1;
+  for (int ply = 0; ply < first_plies; ++ply) bound = bound * 218 < cap ? bound * 218 : cap;
+  for (int ply = first_plies; ply < max_plies; ++ply) {
     {
       LaunchScope ls(e, KC_MOVEGEN);
-      k_bfs_ply<<<max_grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair, sh);
+      if (e->perft_pdl)
+        CRL_CUDA(launch_dependent(k_bfs_ply, dim3(max_grid), dim3(RULES_BLOCK), e->stream, buf0, buf1, cap, ctl, min_frontier,
+                                  depth, pair, sh));
+      else
+        k_bfs_ply<<<max_grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, min_frontier, depth, pair, sh);
       CRL_CUDA(cudaGetLastError());
     }
     bound = bound * 218 < cap ? bound * 218 : cap;
@@ -691,7 +725,11 @@ int launch_perft_root(crl_engine_impl* e, const u64* root, u64* buf0, u64* buf1,
       else k_perft_pair<0, 6><<<pgrid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth);
     }
   }
-  k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk, pair, sh);
+  if (e->perft_pdl && !pair)
+    CRL_CUDA(launch_dependent(k_perft_walk, dim3(grid), dim3(RULES_BLOCK), e->stream, (const u64*)buf0, (const u64*)buf1, cap,
+                              ctl, depth, bulk, pair, sh));
+  else
+    k_perft_walk<<<grid, RULES_BLOCK, 0, e->stream>>>(buf0, buf1, cap, ctl, depth, bulk, pair, sh);
   CRL_CUDA(cudaGetLastError());
   return CRL_OK;
 }

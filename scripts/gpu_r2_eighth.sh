@@ -10,3 +10,13 @@ for tool in memcheck racecheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python scripts/reuse_sanitize.py > gpurun_out/sanitize_reuse_$tool.log 2>&1
   echo "== $tool: $? at $((SECONDS-T0)) s"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|evaluator:|network:|workload ok" gpurun_out/sanitize_reuse_$tool.log | tail -5
 done
+unset CRL_NO_GRAPH
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'k_(bfs_first|bfs_ply|perft_walk)' -c 60 --csv --log-file gpurun_out/launches_perft.csv \
+   python scripts/perft_root_probe.py > gpurun_out/ncu_perft.log 2>&1; echo "== ncu perft launch list: $? at $((SECONDS-T0)) s"
+python - <<'PY'
+import csv
+rows = [r for r in csv.reader(l for l in open("gpurun_out/launches_perft.csv") if not l.startswith("=="))]
+h = rows[0]; kn, mv, mu = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
+for r in rows[1:21]:
+    print(r[kn].split("(")[0][:30], r[mv], r[mu])
+PY
