@@ -56,7 +56,8 @@ def play_game(agent, max_iters=900):
 
 
 def edge_slots_per_node(lanes, nodes, device=None, bytes_per_edge=24, share=0.5):
-    """Edge-pool sizing for long runs: every tree node reserves one edge slot per legal move of its position, and no
+    """(bytes_per_edge: 24 for the seven edge arrays, 32 with evaluation reuse, which keeps the previous tree's child /
+    prior arrays as well.)  Edge-pool sizing for long runs: every tree node reserves one edge slot per legal move of its position, and no
     chess position has more than 218 legal moves, so 218 slots per node can never overflow.  That is what a run gets
     whenever it fits in `share` of the free device memory (4,096 lanes x 901 nodes: 19 GB of a B200's 180 GB);
     otherwise as many as fit (an overflow is then reported as CRL_ENOMEM, never silent)."""
@@ -106,7 +107,7 @@ class LockstepRun:
         self._own_engine = engine is None
         self.eng = engine if engine is not None else Engine(
             max_games=lanes, max_nodes=sims + 1, device=device, max_inflight=threads,
-            avg_moves=edge_slots_per_node(lanes, sims + 1, device))
+            avg_moves=edge_slots_per_node(lanes, sims + 1, device, bytes_per_edge=32 if reuse and threads == 1 else 24))
         if evaluator is None:
             if model is not None:
                 self.eng.load_weights(model.weights)
