@@ -34,19 +34,27 @@ def compute_policy(child_visits, root_visits, n_plies, noise=True):
     return policy
 
 
-_POW_CACHE = {}
+_POW_TABLES = {}
+
+
+def _tempered_table(n_plies, upto):
+    """table[c] = np.power(c, 1 / tau) for c = 0..upto, every entry computed by the very scalar call compute_policy makes
+    (a vectorised np.power may round differently from the scalar one), cached per ply count for the whole run."""
+    n = int(n_plies)
+    t = _POW_TABLES.get(n)
+    if t is None or len(t) <= upto:
+        if len(_POW_TABLES) > 4096:
+            _POW_TABLES.clear()
+        tau = n / (1 + np.power(n, 1.3))
+        have = 0 if t is None else len(t)
+        more = np.array([np.power(c, 1 / tau) for c in range(have, max(upto + 1, 2 * have, 64))], dtype=np.float64)
+        t = _POW_TABLES[n] = more if t is None else np.concatenate([t, more])
+    return t
 
 
 def _tempered(n_plies, count):
     """np.power(count, 1 / tau) exactly as compute_policy evaluates it (same scalar call), memoised."""
-    key = (int(n_plies), int(count))
-    v = _POW_CACHE.get(key)
-    if v is None:
-        if len(_POW_CACHE) > (1 << 20):
-            _POW_CACHE.clear()
-        tau = key[0] / (1 + np.power(key[0], 1.3))
-        v = _POW_CACHE[key] = np.power(key[1], 1 / tau)
-    return v
+    return _tempered_table(n_plies, int(count))[int(count)]
 
 
 def pick_moves(child_visits, n_children, root_visits, n_plies, live, noise=True):
@@ -74,10 +82,12 @@ def pick_moves(child_visits, n_children, root_visits, n_plies, live, noise=True)
     early = pl < 30
     if early.any():                      # tau = 1
         policy[early] = vis[early].astype(np.float64) / rv[early].astype(np.float64)[:, None]
-    for i in np.nonzero(~early)[0]:      # tau = n / (1 + n^1.3): the reference's scalar np.power calls, memoised
-        n = int(pl[i])
-        num = np.array([_tempered(n, v) for v in vis[i, :kr[i]]])
-        policy[i, :kr[i]] = num / _tempered(n, rv[i])
+    late = np.nonzero(~early)[0]
+    if late.size:                        # tau = n / (1 + n^1.3): the reference's scalar np.power results, from per-ply tables
+        uniq, inv = np.unique(pl[late], return_inverse=True)
+        top = int(max(vis[late].max(), rv[late].max()))
+        tables = np.stack([_tempered_table(n, top)[:top + 1] for n in uniq])
+        policy[late] = tables[inv[:, None], vis[late]] / tables[inv, rv[late]][:, None]
     if noise:
         g = np.random.standard_gamma(0.03, size=int(kr.sum()))
         pad = np.zeros((rows.size, kmax), dtype=np.float64)
