@@ -449,6 +449,7 @@ static constexpr int V2_B_BYTES = 128 * BLOCK_K * 2;      // 16 KB: this CTA's h
 static constexpr int V2_STAGE_BYTES = V2_A_BYTES + V2_B_BYTES;
 static constexpr int V2_SMEM_BYTES = 1024 + V2_STAGES * V2_STAGE_BYTES + 2 * TILE_N * 4 + 3 * 256 * 4 + 64 + 512;
 static constexpr uint32_t V2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TILE_N >> 3) << 17) | ((256u >> 4) << 24);
+static constexpr uint32_t V2_IDESC_N128 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
 static constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;        // clears the CTA-rank bit of a shared::cluster address
 
 struct ConvParams2 {
@@ -797,6 +798,12 @@ struct TrunkParams {
   // L2 eviction priorities of the v4 tower's TMA loads: the planes are read once (evict first), the weights are re-read
   // by every CTA pair for every group (evict last), the activation scratch keeps the default
   uint64_t hint_planes, hint_weights;
+  // TIMING PROBE ONLY (CRL_T4_NSPLIT_PROBE=1, scripts/trunk4_nsplit_probe.py): issue every K step as two M=256 x N=128
+  // MMAs (filter halves of the weight stage, accumulator columns 0-127 / 128-255) instead of one N=256 MMA.  The
+  // accumulator columns come out permuted, so the network's RESULTS ARE WRONG in this mode; it exists to measure whether
+  // N=128 MMAs with both operands in shared memory (the image operand read twice) sustain the N=256 rate -- the
+  // precondition of sharing a weight stage between the two tiles of a group.
+  int probe_nsplit;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
@@ -1171,8 +1178,17 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
               const int dy = tap / 3, dx = tap - 3 * dy;                 // already offset by +1
               const uint64_t da = make_kmajor_sw128_desc_sbo(img + (uint32_t)(dy * 20 + dx) * 128u, 1280u);
               const uint64_t db = make_kmajor_sw128_desc(smem_u32(smem_b + bs * T4_B_BYTES));
+              if (p.probe_nsplit) {
+                // (timing probe, see TrunkParams) rows 64..127 of this CTA's weight tile start 8 KB = 512 x 16 B further on
 #pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC, (kc | tap | k) != 0);
+                for (int k = 0; k < BLOCK_K / 16; ++k) {
+                  umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC_N128, (kc | tap | k) != 0);
+                  umma2_bf16(tmem_d + 128, da + 2 * k, db + 512 + 2 * k, V2_IDESC_N128, (kc | tap | k) != 0);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / 16; ++k) umma2_bf16(tmem_d, da + 2 * k, db + 2 * k, V2_IDESC, (kc | tap | k) != 0);
+              }
               umma2_commit_both(&b_empty[bs]);
               if (++bs == T4_NB) {
                 bs = 0;
@@ -1422,6 +1438,7 @@ struct NetWeights {
   // v4 (tower kernel with the padded-image A operand reused across the nine taps)
   bool use_trunk4 = true;
   int t4_ring = 0;                          // index into the instantiated (image slots, weight stages) pairs
+  int probe_nsplit = 0;                     // CRL_T4_NSPLIT_PROBE=1: timing probe, WRONG results (see TrunkParams)
   __nv_bfloat16* act4[2] = {nullptr, nullptr};  // [n_sms/2 pairs x 8 boards][64][256]: ping-pong scratch by CTA-pair slot
   int act4_rows = 0;
   bool l2_hints = true;                     // CRL_T4_L2_HINTS=0 turns the eviction-priority hints off (A/B)
@@ -1571,6 +1588,8 @@ int net_create(crl_engine_impl* e) {
   {
     const char* r = getenv("CRL_T4_RING");   // tuning knob: 0 = 3/7 (default), 1 = 3/8, 2 = 2/9, 3 = 2/10
     nw->t4_ring = r ? atoi(r) : 0;
+    const char* np_ = getenv("CRL_T4_NSPLIT_PROBE");
+    nw->probe_nsplit = (np_ && np_[0] == '1') ? 1 : 0;
     if (nw->t4_ring < 0 || nw->t4_ring > 3) nw->t4_ring = 0;
     const char* h = getenv("CRL_T4_L2_HINTS");
     nw->l2_hints = !(h && h[0] == '0');
@@ -1886,6 +1905,7 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     tp.dbg_layer = dbg_layer;
     tp.hint_planes = nw->l2_hints ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     tp.hint_weights = nw->l2_hints ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    tp.probe_nsplit = nw->probe_nsplit;
     int groups = ((n_host + 3) / 4 + 1) / 2;
     int pairs = groups < nw->n_sms / 2 ? groups : nw->n_sms / 2;
     if (pairs < 1) pairs = 1;
