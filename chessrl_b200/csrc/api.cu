@@ -260,6 +260,11 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   P.NN = e->NN;
   P.EA = e->EA;
   P.K = 1;
+  P.path_cap = 32;
+  if (const char* pc = getenv("CRL_PATH_CAP")) {
+    const int v = atoi(pc);
+    if (v >= 0 && v <= 32) P.path_cap = v;
+  }
   const size_t G = e->G, R = e->R;
   int rc = CRL_OK;
 #define A(field, count) if (rc == CRL_OK) rc = pool_alloc(e, &P.field, (size_t)(count))

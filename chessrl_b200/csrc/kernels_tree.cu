@@ -310,9 +310,9 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
     node = P.e_child[(long long)g * P.EA + e];
   }
   if (term) {
-    if (depth <= 32) P.s_path[(long long)g * 32 + lane] = my_edge;
+    if (depth <= P.path_cap) P.s_path[(long long)g * 32 + lane] = my_edge;
     if (lane == 0) {
-      P.s_depth[g] = depth <= 32 ? depth : -1;
+      P.s_depth[g] = depth <= P.path_cap ? depth : -1;
       P.s_node[g] = node;
       P.s_kind[g] = KIND_TERMINAL;
     }
@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
     const int e = pn.edge0 + pn.n_exp;         // the edge the new child is about to take
     if (lane == (depth & 31)) my_edge = e;
     ++depth;
-    if (depth <= 32) P.s_path[(long long)g * 32 + lane] = my_edge;
-    if (lane == 0) P.s_depth[g] = depth <= 32 ? depth : -1;
+    if (depth <= P.path_cap) P.s_path[(long long)g * 32 + lane] = my_edge;
+    if (lane == 0) P.s_depth[g] = depth <= P.path_cap ? depth : -1;
   }
   int child, twin, n1;
   int kind = expand_child_warp(P, g, g, node, lane, &child, &twin, &n1);

@@ -86,7 +86,8 @@ struct Pools {
   int* s_nmoves;    // [G*K]
   int* s_row;       // [G*K] row of this slot in the current evaluation batch
   int* s_path;      // [G][32] exact schedule: edge (index inside the game's arena) taken at every level of the select
-  int* s_depth;     // [G] levels recorded in s_path, -1 = deeper than 32 (the backup then chases parent pointers)
+  int* s_depth;     // [G] levels recorded in s_path, -1 = deeper than path_cap (the backup then chases parent pointers)
+  int path_cap;     // 32; CRL_PATH_CAP=n (0..32) lowers it so that tests exercise both backup forms in one search
   int* s_wave_n;    // [G] slots used by the current wave
   int* g_sims_left; // [G] simulations of the current crl_mcts_simulate call still to run (wave mode)
   int* eval_list;   // [G*K] slot of every batch row

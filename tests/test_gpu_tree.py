@@ -249,3 +249,58 @@ def test_search_from_unreachable_roots_matches_oracle():
                     line.append(B.move_to_uci(st["replies"][g, k]))
                 assert line == [str(x) for x in c.state.board.move_stack], (fen, k)
         e.close()
+
+
+def _search_all(engine, recs, mls, sims, inflight=1):
+    engine.games_set(recs, mls)
+    engine.mcts_begin_move()
+    engine.mcts_simulate(sims, inflight)
+    st = engine.root_stats()
+    dumps = [[(n.parent, n.slot, n.n_legal, n.n_children, n.result, n.move, n.reply, n.visits, float(n.value), float(n.prior))
+              for n in engine.node_dump(g)] for g in (0, 1, len(recs) - 1)]
+    return st, dumps
+
+
+def test_level_parallel_backup_equals_the_parent_chase(monkeypatch):
+    """The backup of a simulation runs at the head of the next k_select_expand, one lane per level of the path the select
+    recorded; paths deeper than the recorded levels fall back to the parent-pointer chase.  CRL_PATH_CAP lowers the number
+    of recorded levels: 32 (default), 2 (both forms inside one search) and 0 (chase only) must give the same trees."""
+    from chessrl_b200.engine import Engine
+    recs = np.tile(B.record_from_fen(), (24, 1))
+    mls = [[B.uci_to_move(m) for m in (["e2e4", "e7e5", "g1f3"][:g % 4])] for g in range(24)]
+    out = []
+    for cap in ("32", "2", "0"):
+        monkeypatch.setenv("CRL_PATH_CAP", cap)
+        e = Engine(max_games=24, max_nodes=161, avg_moves=96)
+        e.set_evaluator(EVAL_HASH, 17, 7)          # 7-bit priors, values in a narrow band: the search digs deep lines
+        out.append(_search_all(e, recs, mls, 160))
+        e.close()
+    depth = max(len([1 for n in d if n[3] > 0]) for d in out[0][1])
+    assert depth >= 3
+    for st, dumps in out[1:]:
+        for k in ("visits", "values", "priors", "moves", "replies", "results", "n_children", "root_visits", "root_values"):
+            assert np.array_equal(st[k], out[0][0][k]), k
+        assert dumps == out[0][1]
+
+
+def test_wave_call_followed_by_exact_call_on_the_same_tree():
+    """crl_mcts_simulate may be called several times on one tree, with different numbers of simulations in flight: a wave
+    call leaves nothing in flight (every slot is finished by k_finalize_wave), so the exact-schedule call that follows
+    starts clean, and its own last simulation is finished before the call returns (k_finalize)."""
+    from chessrl_b200.engine import Engine
+    e = Engine(max_games=16, max_nodes=200, avg_moves=96, max_inflight=8)
+    e.set_evaluator(EVAL_HASH, 2, 24)
+    e.games_set(np.tile(B.record_from_fen(), (16, 1)))
+    e.mcts_begin_move()
+    total = 0
+    for sims, k in ((40, 8), (30, 1), (24, 4), (1, 1), (25, 1)):
+        e.mcts_simulate(sims, k)
+        total += sims
+        st = e.root_stats(want=("visits",))
+        assert (st["root_visits"] == 1 + total).all()
+        assert (st["visits"].sum(axis=1) == total).all()
+        nodes = e.node_dump(3)
+        assert len(nodes) == 1 + total and sum(n.visits for n in nodes if n.parent == 0) == total
+    c = e.counters()
+    assert c["simulations"] == 16 * total
+    e.close()
