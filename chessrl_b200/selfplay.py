@@ -275,6 +275,9 @@ def main(argv=None):
                 logger.info("\tTraining %d of %d" % (i + 1, len(data)))
                 agent.train(DatasetGame([g]), logdir=args.model_dir, epochs=1, validation_split=0, batch_size=1)
             agent.save(model_path)
+    if world > 1:
+        from . import sharding
+        sharding.shutdown()
 
 
 if __name__ == "__main__":

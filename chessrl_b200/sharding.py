@@ -24,6 +24,12 @@ def init(backend=None):
     dist.init_process_group(backend)
 
 
+def shutdown():
+    """Leave the process group (a run that exits without doing so gets a resource-leak warning from NCCL)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def _dev():
     return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
