@@ -303,6 +303,47 @@ def whole_games_complete_run(model_pack, n_games, lanes, sims, inflight, seed, r
     return stats
 
 
+def training_step_leg(pack, n_positions=640, steps=10, warmup=3):
+    """the training step behind Agent.train (chessrl_b200/training.py: Keras loss, tf.keras Adam,
+    BatchNorm in training mode; PyTorch fp32 WITHOUT TF32, like the reference's fp32 TensorFlow -- north_star allows
+    PyTorch here) on a synthetic batch the size of 8 games x 80 plies, timed with CUDA events.  Reported against the
+    forward + backward arithmetic (3 x the network's forward FLOPs); not a tensor-core path by construction (fp32)."""
+    import torch
+    from chessrl_b200 import training
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(3)
+    planes = (torch.rand((n_positions, 8, 8, 128), device=dev, generator=g) < 0.15).to(torch.bfloat16)
+    planes[..., 127] = 0
+    pol = torch.randint(0, 1968, (n_positions,), device=dev, generator=g)
+    val = torch.randint(-1, 2, (n_positions,), device=dev, generator=g).float()
+    out = {}
+    for precision in training.PRECISIONS:
+        params = [torch.tensor(w, device=dev) for w in pack]
+        trainable = []
+        for i in training.trainable_indices():
+            params[i].requires_grad_(True)
+            trainable.append(params[i])
+        opt = training.KerasAdam(trainable, lr=0.002, epsilon=1e-7)
+        with training.arithmetic(precision):
+            for _ in range(warmup):
+                training.train_step(params, opt, planes, pol, val)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(steps):
+                rec = training.train_step(params, opt, planes, pol, val)
+            b.record()
+            torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out[precision] = {"ms_per_step": ms, "positions_per_s": n_positions / (ms * 1e-3),
+                          "tflops": 3 * NET_FLOP_PER_POS * n_positions / (ms * 1e-3) / 1e12, "last_loss": rec["loss"]}
+    return {"workload": "one training step (forward in training mode + backward + Adam) on %d synthetic positions = 8 games x 80 "
+                        "plies (PyTorch / cuDNN; SURVEY.md 8f rank 1); fp32 without TF32 is the default and the parity setting, "
+                        "tf32 / bf16 autocast are opt-in (CRL_TRAIN_PRECISION)" % n_positions,
+            "ms_per_step": out["fp32"]["ms_per_step"], "positions_per_s": out["fp32"]["positions_per_s"],
+            "tflops_fp32": out["fp32"]["tflops"], "by_precision": out}
+
+
 def large_config(pack, world, rank, dist, barrier, K):
     """BASELINE configs[4] (65,536 games x 800 sims/move sharded by game over the ranks) when there are >= 2 ranks;
     on one GPU the >= 65k-concurrent-games claim: 65,536 games x 200 sims/move.  One timed step after a short warm-up."""
@@ -595,6 +636,7 @@ def main():
     ap.add_argument("--no-whole-games", action="store_true", help="skip the steady-state whole-game leg")
     ap.add_argument("--wg-steps", type=int, default=10, help="lockstep moves timed in the steady-state whole-game leg")
     ap.add_argument("--no-large", action="store_true", help="skip the configs[4] / 65,536-games leg")
+    ap.add_argument("--no-training", action="store_true", help="skip the training-step leg")
     ap.add_argument("--whole-games", type=int, default=0, help="also play this many COMPLETE games (drain included)")
     ap.add_argument("--wg-lanes", type=int, default=None)
     ap.add_argument("--wg-sims", type=int, default=None)
@@ -770,6 +812,9 @@ def main():
             whole_reuse["speedup_over_no_reuse"] = whole_reuse["simulations_per_s"] / whole["simulations_per_s"]
     if rank == 0 and args.whole_games > 0:
         complete = whole_games_complete_run(pack, args.whole_games, args.wg_lanes or G, args.wg_sims or S, K, seed=7)
+    train_leg = None
+    if rank == 0 and not args.no_training:
+        train_leg = training_step_leg(pack)
     if not args.no_large:
         large = large_config(pack, world, rank, dist, barrier, K)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -799,7 +844,7 @@ def main():
             "evaluations_per_simulation": evals_all / max(1.0, sims_dev),
             "net_tflops_in_step": evals_all * NET_FLOP_PER_POS / (ms_dev * 1e-3) / 1e12 / world,
             "roofline": roof, "cpu_baseline": cpu, "perft": perft, "perft_sharded": perft_multi, "kernels": kernels,
-            "whole_games": whole, "whole_games_reuse": whole_reuse, "whole_games_complete_run": complete, "large_config": large,
+            "whole_games": whole, "whole_games_reuse": whole_reuse, "whole_games_complete_run": complete, "large_config": large, "training_step": train_leg,
         }
         print(json.dumps(line))
     if world > 1:

@@ -232,7 +232,11 @@ def main(argv=None):
     parser.add_argument('--no-reuse', action='store_true', default=False,
                         help="evaluate every position of every search (default: evaluations of the previous move's "
                              "search are reused; the games are identical either way)")
+    parser.add_argument('--precision', choices=("fp32", "tf32", "bf16"), default=None,
+                        help="arithmetic of the training step (default fp32 = the parity setting; see chessrl_b200/training.py)")
     args = parser.parse_args(argv)
+    if args.precision:
+        os.environ["CRL_TRAIN_PRECISION"] = args.precision
 
     logger = Logger.get_instance()
     logger.set_level(0 if args.debug else 1)

@@ -10,6 +10,7 @@ the same name; the same command-line flags.  The training step itself is chessrl
 from __future__ import annotations
 
 import argparse
+import os
 
 from .agent import Agent
 from .dataset import DatasetGame
@@ -24,6 +25,9 @@ _FLAGS = (
     (("--epochs",), dict(metavar="epochs", type=int, default=1)),
     (("--bs",), dict(metavar="bs", type=int, default=8, help="Batch size. Default 8")),
     (("--debug",), dict(action="store_true", default=False, help="Log debug messages on screen. Default false.")),
+    (("--precision",), dict(choices=("fp32", "tf32", "bf16"), default=None,
+                            help="arithmetic of the training step (default fp32 = the parity setting; tf32 / bf16 run the "
+                                 "convolutions on the tensor cores, 8-10 x faster, gradients no longer parity-grade)")),
 )
 
 
@@ -59,6 +63,8 @@ def main(argv=None):
         cli.add_argument(*names, **options)
     opts = cli.parse_args(argv)
     Logger.get_instance().set_level(0 if opts.debug else 1)
+    if opts.precision:
+        os.environ["CRL_TRAIN_PRECISION"] = opts.precision
     train(opts.model_dir, opts.data_path, epochs=opts.epochs, batch_size=opts.bs)
 
 

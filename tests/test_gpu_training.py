@@ -99,3 +99,40 @@ def test_agent_train_runs_batched_with_validation(golden, tmp_path, capsys):
     assert np.isfinite(vals[0]["val_loss"]) and "val_loss" in capsys.readouterr().out
     moved = sum(float(np.abs(a - b).max()) > 0 for a, b in zip(agent.model.weights, before))
     assert moved >= 90                                          # every kernel / bias / gamma / beta and the BN statistics
+
+
+def test_opt_in_precisions_leave_the_default_alone_and_agree_on_the_loss(monkeypatch):
+    """fp32 without TF32 is the default and the only parity-grade setting; CRL_TRAIN_PRECISION = tf32 / bf16 are opt-in
+    throughput settings: same loss to 1e-4 relative on the same batch, finite gradients, and the process-wide TF32
+    switches are back where they were afterwards."""
+    dev = torch.device("cuda")
+    pack = model.random_pack(4, perturb_bn=True)
+    g = torch.Generator(device=dev).manual_seed(1)
+    n = 96
+    planes = (torch.rand((n, 8, 8, 128), device=dev, generator=g) < 0.15).to(torch.bfloat16)
+    planes[..., 127] = 0
+    pol = torch.randint(0, 1968, (n,), device=dev, generator=g)
+    val = torch.randint(-1, 2, (n,), device=dev, generator=g).float()
+    monkeypatch.delenv("CRL_TRAIN_PRECISION", raising=False)
+    assert training.resolve_precision() == "fp32"
+    monkeypatch.setenv("CRL_TRAIN_PRECISION", "tf32")
+    assert training.resolve_precision() == "tf32" and training.resolve_precision("bf16") == "bf16"
+    with pytest.raises(ValueError):
+        training.resolve_precision("fp8")
+    before = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    losses = {}
+    for precision in training.PRECISIONS:
+        params = [torch.tensor(w, device=dev) for w in pack]
+        tr = []
+        for i in training.trainable_indices():
+            params[i].requires_grad_(True)
+            tr.append(params[i])
+        with training.arithmetic(precision):
+            assert torch.backends.cudnn.allow_tf32 == (precision == "tf32")
+            total, _, _, _, _ = training.loss_terms(params, planes, pol, val, training=True)
+            grads = torch.autograd.grad(total, tr)
+        assert all(torch.isfinite(x).all() for x in grads) and all(x.dtype == torch.float32 for x in grads)
+        losses[precision] = float(total.detach())
+    assert (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32) == before
+    for precision in ("tf32", "bf16"):
+        assert abs(losses[precision] - losses["fp32"]) <= 1e-4 * abs(losses["fp32"]), losses
