@@ -33,7 +33,11 @@ _KERNEL_IDX = None
 # cores: measured on a B200, 640 positions per step: fp32 103.5 ms, tf32 12.6 ms (8.2 x), bf16 autocast 9.9 ms (10.5 x);
 # the loss agrees to 1e-6 / 1e-5 relative, individual gradient tensors of the 21-layer tower deviate by up to 13 % / 39 %
 # of their largest entry on a random-init pack (scripts/probe/train_precision_probe.py) -- NOT parity-grade, hence opt-in.
-PRECISIONS = ("fp32", "tf32", "bf16")
+# "tf32x3" keeps fp32-grade numerics ON the tensor cores: every convolution operand is split into a TF32-representable
+# head and its (exact) fp32 remainder, x = x_hi + x_lo, and x * w is evaluated as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with
+# fp32 accumulation -- three TF32 convolutions instead of one fp32 convolution on the CUDA cores, forward and both
+# backward passes (the dropped x_lo*w_lo term is below 2^-22 of the product).  See _Conv3xTF32.
+PRECISIONS = ("fp32", "tf32x3", "tf32", "bf16")
 
 
 def resolve_precision(precision=None):
@@ -47,12 +51,60 @@ def resolve_precision(precision=None):
 def arithmetic(precision):
     """TF32 switches (and bf16 autocast) for the duration of a training / validation pass, restored afterwards."""
     saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+    global _CONV_SPLIT
+    saved_split = _CONV_SPLIT
+    torch.backends.cudnn.allow_tf32 = precision in ("tf32", "tf32x3")     # tf32x3: convolutions only, on split operands
+    torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+    _CONV_SPLIT = precision == "tf32x3"
     try:
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=precision == "bf16"):
             yield
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        _CONV_SPLIT = saved_split
+
+
+_CONV_SPLIT = False
+
+
+def _tf32_split(x):
+    """x = hi + lo with hi representable in TF32 (10 explicit mantissa bits, round half up in magnitude) and lo the exact
+    fp32 remainder."""
+    hi = ((x.contiguous().view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+    return hi, x - hi
+
+
+class _Conv3xTF32(torch.autograd.Function):
+    """conv2d (stride 1, 'same' padding) whose three passes each run as three TF32 tensor-core convolutions on split
+    operands (see PRECISIONS): fp32-grade results at roughly a third of the fp32 CUDA-core time."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, padding):
+        ctx.save_for_backward(x, w)
+        ctx.padding = padding
+        xh, xl = _tf32_split(x)
+        wh, wl = _tf32_split(w)
+        y = F.conv2d(xh, wh, None, padding=padding)
+        y = y + F.conv2d(xh, wl, None, padding=padding)
+        y = y + F.conv2d(xl, wh, None, padding=padding)
+        return y + b.view(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        pad = ctx.padding
+        gh, gl = _tf32_split(gy)
+        xh, xl = _tf32_split(x)
+        wh, wl = _tf32_split(w)
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gi = torch.nn.grad.conv2d_input
+            gx = gi(x.shape, wh, gh, padding=pad) + gi(x.shape, wl, gh, padding=pad) + gi(x.shape, wh, gl, padding=pad)
+        if ctx.needs_input_grad[1]:
+            gwf = torch.nn.grad.conv2d_weight
+            gw = gwf(xh, w.shape, gh, padding=pad) + gwf(xh, w.shape, gl, padding=pad) + gwf(xl, w.shape, gh, padding=pad)
+        gb = gy.sum(dim=(0, 2, 3)) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None
 
 
 def _kernel_indices():
@@ -72,6 +124,8 @@ def forward_logits(p, planes_nhwc, training):
     x = planes_nhwc[..., :127].permute(0, 3, 1, 2).float()
 
     def conv(x, i):
+        if _CONV_SPLIT:
+            return _Conv3xTF32.apply(x, p[i].permute(3, 2, 0, 1), p[i + 1], p[i].shape[0] // 2)
         return F.conv2d(x, p[i].permute(3, 2, 0, 1), p[i + 1], padding=p[i].shape[0] // 2)
 
     x = conv(x, 0)

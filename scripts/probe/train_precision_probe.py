@@ -30,15 +30,14 @@ def fresh():
 
 def grads_of(mode):
     params, tr = fresh()
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
-    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+    with training.arithmetic(mode):
         total, lp, lv, reg, _ = training.loss_terms(params, planes, pol, val, training=True)
-    gr = torch.autograd.grad(total, tr)
+        gr = torch.autograd.grad(total, tr)
     return float(total.detach()), float(lp.detach()), float(lv.detach()), [x.float() for x in gr]
 
 
 ref = grads_of("fp32")
-for mode in ("fp32", "tf32", "bf16"):
+for mode in ("fp32", "tf32x3", "tf32", "bf16"):
     t, lp, lv, gr = grads_of(mode)
     # (the bias of a convolution that feeds a BatchNorm has a mathematically zero gradient: what fp32 reports for it is
     #  rounding noise, so tensors whose reference gradient is below 1e-4 of the largest one are compared on that scale)
@@ -51,12 +50,11 @@ for mode in ("fp32", "tf32", "bf16"):
     print("   %d live tensors, %d with (near-)zero gradients: their worst |error| / largest gradient = %.2e" % (len(live), len(dead), dead_abs))
     params, tr = fresh()
     opt = training.KerasAdam(tr)
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
 
     def step():
-        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=mode == "bf16"):
+        with training.arithmetic(mode):
             total, _, _, _, _ = training.loss_terms(params, planes, pol, val, training=True)
-        opt.step(list(torch.autograd.grad(total, tr)))
+            opt.step(list(torch.autograd.grad(total, tr)))
 
     for _ in range(3):
         step()

@@ -67,19 +67,19 @@ def test_encode_games_flips_planes_but_not_the_policy_target(golden):
         assert val.tolist() == [0.0 if v is None else float(v) for v in case["values"]]
 
 
-def test_training_step_on_the_device_matches_fp64_restatement():
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+def test_training_step_on_the_device_matches_fp64_restatement(precision):
+    """fp32 on the CUDA cores (the default) and tf32x3 -- three TF32 tensor-core convolutions on split operands per
+    convolution pass -- are both held to the same bounds against the fp64 restatement of the Keras definitions."""
     import train_ref
     from test_training_step import _batch
     pack = model.random_pack(seed=21, perturb_bn=True)
     x, pol, val = _batch(n_positions=24, seed=6)
     tr = training.trainable_indices()
     ref = train_ref.loss_and_grads(pack, x, pol, val, tr)
-    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
-    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
-    try:
+    with training.arithmetic(precision):
+        assert torch.backends.cuda.matmul.allow_tf32 is False
         check_against_ref(pack, x, pol, val, tr, *ref, device="cuda")
-    finally:
-        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def test_agent_train_runs_batched_with_validation(golden, tmp_path, capsys):
@@ -128,7 +128,7 @@ def test_opt_in_precisions_leave_the_default_alone_and_agree_on_the_loss(monkeyp
             params[i].requires_grad_(True)
             tr.append(params[i])
         with training.arithmetic(precision):
-            assert torch.backends.cudnn.allow_tf32 == (precision == "tf32")
+            assert torch.backends.cudnn.allow_tf32 == (precision in ("tf32", "tf32x3"))
             total, _, _, _, _ = training.loss_terms(params, planes, pol, val, training=True)
             grads = torch.autograd.grad(total, tr)
         assert all(torch.isfinite(x).all() for x in grads) and all(x.dtype == torch.float32 for x in grads)
@@ -136,3 +136,4 @@ def test_opt_in_precisions_leave_the_default_alone_and_agree_on_the_loss(monkeyp
     assert (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32) == before
     for precision in ("tf32", "bf16"):
         assert abs(losses[precision] - losses["fp32"]) <= 1e-4 * abs(losses["fp32"]), losses
+    assert abs(losses["tf32x3"] - losses["fp32"]) <= 2e-6 * abs(losses["fp32"]), losses

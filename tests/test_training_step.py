@@ -89,6 +89,18 @@ def test_loss_gradients_and_bn_statistics_match_fp64_restatement(step_data):
     check_against_ref(*step_data, device="cpu")
 
 
+def test_split_convolution_step_matches_fp64_restatement(step_data):
+    """The tf32x3 setting (training._Conv3xTF32: x*w as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi in all three convolution
+    passes) against the same fp64 restatement and the same bounds.  On the CPU the three partial convolutions run in
+    fp32, so this checks the decomposition and its hand-written backward; the GPU test runs them on the tensor cores."""
+    hi, lo = training._tf32_split(torch.tensor([1.0000001, -3.14159265, 1e-20, 123456.789, 0.0]))
+    assert torch.equal(hi + lo, torch.tensor([1.0000001, -3.14159265, 1e-20, 123456.789, 0.0]))
+    assert (hi.view(torch.int32) & 0x1FFF).abs().sum() == 0               # 13 low mantissa bits clear: TF32-representable
+    assert (lo.abs() <= hi.abs() * 2.0 ** -11 + 1e-45).all()
+    with training.arithmetic("tf32x3"):
+        check_against_ref(*step_data, device="cpu")
+
+
 def test_keras_adam_update_matches_definition():
     rng = np.random.default_rng(0)
     ws = [rng.normal(size=s).astype(np.float32) for s in ((3, 3, 4, 5), (7,), (11, 2))]
