@@ -121,7 +121,7 @@ def _bn(x, p, o, training):
 
 def forward_logits(p, planes_nhwc, training):
     """p: list of 140 tensors (pack order).  Returns (policy logits [B,1968], value [B])."""
-    x = planes_nhwc[..., :127].permute(0, 3, 1, 2).float()
+    x = planes_nhwc[..., :127].permute(0, 3, 1, 2).to(p[0].dtype)    # fp32 (fp64 when a probe passes double parameters)
 
     def conv(x, i):
         if _CONV_SPLIT:

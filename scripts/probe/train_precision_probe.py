@@ -1,5 +1,6 @@
-"""Probe: the training step (chessrl_b200/training.py) at fp32 (the parity setting), with TF32 convolutions / matmuls, and
-under bf16 autocast: time per step and the deviation of loss / gradients from the fp32 step on the same batch."""
+"""Probe: the training step (chessrl_b200/training.py) at fp32 (the parity setting), tf32x3 (three TF32 tensor-core
+convolutions on split operands per convolution pass), with plain TF32 convolutions / matmuls, and under bf16 autocast:
+time per step and the deviation of loss / gradients from the SAME step in float64 on the same batch."""
 import os
 import sys
 
@@ -36,9 +37,23 @@ def grads_of(mode):
     return float(total.detach()), float(lp.detach()), float(lv.detach()), [x.float() for x in gr]
 
 
-ref = grads_of("fp32")
+def grads_fp64():
+    """The same step in float64 on the GPU: the yardstick (fp32 itself is only good to ~1e-2 of a gradient tensor's largest
+    entry on this 21-layer tower with batch statistics)."""
+    params = [torch.tensor(w, device=dev).double() for w in pack]
+    tr = []
+    for i in training.trainable_indices():
+        params[i].requires_grad_(True)
+        tr.append(params[i])
+    total, lp, lv, reg, _ = training.loss_terms(params, planes, pol, val.double(), training=True)
+    gr = torch.autograd.grad(total, tr)
+    return float(total.detach()), float(lp.detach()), float(lv.detach()), [x.double() for x in gr]
+
+
+ref = grads_fp64()
 for mode in ("fp32", "tf32x3", "tf32", "bf16"):
     t, lp, lv, gr = grads_of(mode)
+    gr = [x.double() for x in gr]
     # (the bias of a convolution that feeds a BatchNorm has a mathematically zero gradient: what fp32 reports for it is
     #  rounding noise, so tensors whose reference gradient is below 1e-4 of the largest one are compared on that scale)
     gmax = max(float(b.abs().max()) for b in ref[3])
@@ -66,6 +81,6 @@ for mode in ("fp32", "tf32x3", "tf32", "bf16"):
     b.record()
     torch.cuda.synchronize()
     ms = a.elapsed_time(b) / 10
-    print("%s: %.1f ms per %d-position step = %.0f positions/s; loss %.6f (policy %.6f value %.6f) vs fp32 %.6f; "
-          "gradients vs fp32: worst tensor max-error / max %.2e, L2 %.2e" %
+    print("%s: %.1f ms per %d-position step = %.0f positions/s; loss %.6f (policy %.6f value %.6f) vs fp64 %.6f; "
+          "gradients vs fp64: worst tensor max-error / max %.2e, L2 %.2e" %
           (mode, ms, N, N / ms * 1e3, t, lp, lv, ref[0], worst_max, worst_l2), flush=True)
