@@ -31,12 +31,16 @@ _KERNEL_IDX = None
 # what the loss / gradient / Adam tests pin against the fp64 restatement of the Keras definitions.  "tf32" and "bf16" are
 # opt-in throughput settings (CRL_TRAIN_PRECISION, `--precision` of the CLIs) that put the convolutions on the tensor
 # cores: measured on a B200, 640 positions per step: fp32 103.5 ms, tf32 12.6 ms (8.2 x), bf16 autocast 9.9 ms (10.5 x);
-# the loss agrees to 1e-6 / 1e-5 relative, individual gradient tensors of the 21-layer tower deviate by up to 13 % / 39 %
-# of their largest entry on a random-init pack (scripts/probe/train_precision_probe.py) -- NOT parity-grade, hence opt-in.
+# the loss agrees to 1e-6 / 1e-5 relative, individual gradient tensors of the 21-layer tower deviate from a float64 step by
+# up to 13 % / 39 % of their largest entry on a random-init pack (fp32: 1 %; scripts/probe/train_precision_probe.py) --
+# NOT parity-grade, hence opt-in.
 # "tf32x3" keeps fp32-grade numerics ON the tensor cores: every convolution operand is split into a TF32-representable
 # head and its (exact) fp32 remainder, x = x_hi + x_lo, and x * w is evaluated as x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with
 # fp32 accumulation -- three TF32 convolutions instead of one fp32 convolution on the CUDA cores, forward and both
-# backward passes (the dropped x_lo*w_lo term is below 2^-22 of the product).  See _Conv3xTF32.
+# backward passes (the dropped x_lo*w_lo term is below 2^-22 of the product).  See _Conv3xTF32.  Measured on a B200, 640
+# positions: 41.1 ms per step (2.5 x fp32); loss equal to fp32's to 7 digits; gradients against a float64 step: worst tensor
+# 2.0e-2 of its largest entry / 7.7e-3 in L2, where fp32 itself is at 9.8e-3 / 2.7e-3 (plain tf32: 1.3e-1 / 9.9e-2) -- the
+# tensor cores' fp32 accumulation, not the split, sets that floor.  fp32-grade, still opt-in.
 PRECISIONS = ("fp32", "tf32x3", "tf32", "bf16")
 
 

@@ -56,7 +56,7 @@ def _torch_step(pack, x, pol, val, tr, device="cpu"):
     return params, {"loss": total.item(), "policy_loss": lp.item(), "value_loss": lv.item(), "reg": reg.item()}, grads
 
 
-def check_against_ref(pack, x, pol, val, tr, ref_losses, ref_grads, ref_stats, device="cpu"):
+def check_against_ref(pack, x, pol, val, tr, ref_losses, ref_grads, ref_stats, device="cpu", grad_max=2e-2, grad_l2=4e-3):
     params, losses, grads = _torch_step(pack, x, pol, val, tr, device)
     for k in ("loss", "policy_loss", "value_loss", "reg"):
         assert abs(losses[k] - ref_losses[k]) <= 1e-5 * max(1.0, abs(ref_losses[k])), (k, losses[k], ref_losses[k])
@@ -76,7 +76,7 @@ def check_against_ref(pack, x, pol, val, tr, ref_losses, ref_grads, ref_stats, d
         err = np.abs(g32 - g64).max() / scale
         err_l2 = np.linalg.norm(g32 - g64) / np.linalg.norm(g64)
         worst = max(worst, err)
-        assert err <= 2e-2 and err_l2 <= 4e-3, (i, err, err_l2)
+        assert err <= grad_max and err_l2 <= grad_l2, (i, err, err_l2)
     # BatchNorm moving statistics after the forward pass (momentum 0.99, unbiased batch variance)
     bn_slots = [2 + 12 * b + 6 * s + 4 for b in range(10) for s in range(2)] + [126, 134]
     for slot, (m64, v64) in zip(bn_slots, ref_stats):
