@@ -1055,7 +1055,7 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc_sbo(uint32_t smem_add
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int T4_NA, int T4_NB>
+template <int T4_NA, int T4_NB, bool SINGLE = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __restrict__ maps,
          const LayerDesc* __restrict__ layers, TrunkParams p) {
@@ -1083,7 +1083,14 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
   int n_boards = p.n_host;
   if (p.n_dev) n_boards = min(n_boards, *p.n_dev);
   const int n_tiles = (n_boards + 3) >> 2;          // 256-row tiles (4 boards)
-  const int n_groups = (n_tiles + 1) >> 1;
+  // SINGLE (a separate instantiation, chosen by the host when the batch bound gives every tile a CTA pair of its own:
+  // <= 4 boards per pair -- one game, small lane counts): ONE tile per group.  A second tile would only be padding, and a
+  // pair working through two tiles takes twice as long as two pairs with one each.  (The epilogue then has no other tile's
+  // MMAs to hide behind; the weight stages of the next layer still stream in meanwhile.)  Same arithmetic per tile, same
+  // results.  The two-tile instantiation is untouched (a run-time switch measured 0.5 % slower at 4,096 positions).
+  constexpr bool single = SINGLE;
+  constexpr int XN = SINGLE ? 1 : 2;
+  const int n_groups = single ? n_tiles : (n_tiles + 1) >> 1;
   const int NL = p.n_layers;
 
   if (threadIdx.x == 0) prefetch_tmap(&map_planes);
@@ -1126,8 +1133,8 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
         const LayerDesc ld = layers[L];
         const CUtensorMap* map_a = ld.map_in == 0 ? &map_planes : maps + ld.map_in;
         const CUtensorMap* map_w = maps + ld.map_w;
-        for (int X = 0; X < 2; ++X) {
-          const int tile = 2 * grp + X;
+        for (int X = 0; X < XN; ++X) {
+          const int tile = single ? grp : 2 * grp + X;
           if (L > 0) mbar_wait(&act_ready[X], (uint32_t)((uses - 1) & 1));
           for (int kc = 0; kc < ld.k_chunks; ++kc) {
             mbar_wait(&a_empty[as], aphase ^ 1);
@@ -1165,7 +1172,7 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
     for (int grp = pair; grp < n_groups; grp += n_pairs) {
       for (int L = 0; L < NL; ++L, ++uses) {
         const int k_chunks = layers[L].k_chunks;
-        for (int X = 0; X < 2; ++X) {
+        for (int X = 0; X < XN; ++X) {
           mbar_wait(&tmem_empty[X], (uint32_t)((uses & 1) ^ 1));
           tcgen05_fence_after();
           const uint32_t tmem_d = tmem_base + X * TILE_N;
@@ -1207,7 +1214,7 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
     }
     if (uses > 0) {
       mbar_wait(&tmem_empty[0], (uint32_t)((uses - 1) & 1));
-      mbar_wait(&tmem_empty[1], (uint32_t)((uses - 1) & 1));
+      if (!single) mbar_wait(&tmem_empty[1], (uint32_t)((uses - 1) & 1));
     }
   } else if (warp >= 4) {
     // ================= epilogue (both CTAs) =================
@@ -1224,8 +1231,8 @@ k_trunk4(const __grid_constant__ CUtensorMap map_planes, const CUtensorMap* __re
           s_shift[i] = ld.shift[i];
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int X = 0; X < 2; ++X) {
-          const int tile = 2 * grp + X;
+        for (int X = 0; X < XN; ++X) {
+          const int tile = single ? grp : 2 * grp + X;
           mbar_wait(&tmem_full[X], (uint32_t)(uses & 1));
           tcgen05_fence_after();
           const int board = tile * 4 + (int)rank * 2 + eb;
@@ -1439,6 +1446,7 @@ struct NetWeights {
   bool use_trunk4 = true;
   int t4_ring = 0;                          // index into the instantiated (image slots, weight stages) pairs
   int probe_nsplit = 0;                     // CRL_T4_NSPLIT_PROBE=1: timing probe, WRONG results (see TrunkParams)
+  bool t4_single = true;                    // single-tile instantiation for small batches (CRL_T4_NO_SINGLE=1: off)
   __nv_bfloat16* act4[2] = {nullptr, nullptr};  // [n_sms/2 pairs x 8 boards][64][256]: ping-pong scratch by CTA-pair slot
   int act4_rows = 0;
   bool l2_hints = true;                     // CRL_T4_L2_HINTS=0 turns the eviction-priority hints off (A/B)
@@ -1582,12 +1590,15 @@ int net_create(crl_engine_impl* e) {
   CRL_CUDA(cudaFuncSetAttribute(k_conv_v2, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk, cudaFuncAttributeMaxDynamicSharedMemorySize, V2_SMEM_BYTES));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk4<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(3, 7)));
+  CRL_CUDA(cudaFuncSetAttribute(k_trunk4<3, 7, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(3, 7)));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk4<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(3, 8)));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk4<2, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(2, 9)));
   CRL_CUDA(cudaFuncSetAttribute(k_trunk4<2, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, t4_smem_bytes(2, 10)));
   {
     const char* r = getenv("CRL_T4_RING");   // tuning knob: 0 = 3/7 (default), 1 = 3/8, 2 = 2/9, 3 = 2/10
     nw->t4_ring = r ? atoi(r) : 0;
+    const char* ns_ = getenv("CRL_T4_NO_SINGLE");
+    nw->t4_single = !(ns_ && ns_[0] == '1');
     const char* np_ = getenv("CRL_T4_NSPLIT_PROBE");
     nw->probe_nsplit = (np_ && np_[0] == '1') ? 1 : 0;
     if (nw->t4_ring < 0 || nw->t4_ring > 3) nw->t4_ring = 0;
@@ -1909,9 +1920,16 @@ int net_forward(crl_engine_impl* e, const __nv_bfloat16* planes, int n_host, con
     int groups = ((n_host + 3) / 4 + 1) / 2;
     int pairs = groups < nw->n_sms / 2 ? groups : nw->n_sms / 2;
     if (pairs < 1) pairs = 1;
+    // small batches (every tile of the batch BOUND gets a CTA pair of its own): the single-tile instantiation, one pair per tile
+    const int tiles = (n_host + 3) / 4;
+    const bool single = nw->use_trunk4 && nw->t4_single && tiles <= nw->n_sms / 2;
+    if (single) pairs = tiles < 1 ? 1 : tiles;
     {
       LaunchScope ls(e, KC_CONV);
-      if (nw->use_trunk4) {
+      if (single) {
+        k_trunk4<3, 7, true><<<dim3(2 * pairs), dim3(CONV_THREADS), t4_smem_bytes(3, 7), e->stream>>>(nw->map_planes4, nw->d_maps4,
+                                                                                                  nw->d_layers4, tp);
+      } else if (nw->use_trunk4) {
         const dim3 grid(2 * pairs), block(CONV_THREADS);
         switch (nw->t4_ring) {
           case 1: k_trunk4<3, 8><<<grid, block, t4_smem_bytes(3, 8), e->stream>>>(nw->map_planes4, nw->d_maps4, nw->d_layers4, tp); break;
