@@ -38,6 +38,7 @@ class Engine:
         self.max_games = int(max_games)
         self.max_nodes = int(max_nodes)
         self.max_inflight = int(max_inflight)
+        self.reuse = False               # evaluation reuse across consecutive searches (set_reuse)
         h = vp()
         with torch.cuda.device(self.device):
             stream = torch.cuda.current_stream(self.device).cuda_stream
