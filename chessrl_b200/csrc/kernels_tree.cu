@@ -31,33 +31,40 @@ __device__ __forceinline__ bool game_running(const Pools& P, int g) {
   return P.g_active[g] && P.g_result[g] == RESULT_NONE;
 }
 
-// VL: subtract the children's virtual loss (wave mode; with one in-flight simulation it is always zero)
+// VL: subtract the children's virtual loss (wave mode; with one in-flight simulation it is always zero).
+// Every lane also loads the child index of the edges it scores, so the winner's child comes out of the reduction and the
+// descent does not pay another dependent load per level (`child`, when asked for).
 template <bool VL>
 struct WarpScan {
   const Pools& P;
   int g, lane;
-  __device__ __forceinline__ int operator()(const NodeRec& n) const {
+  __device__ __forceinline__ int operator()(const NodeRec& n, int* child = nullptr) const {
     const long long base = (long long)g * P.EA + n.edge0;
     const int cnt = n.n_exp;
     double best_s = -CUDART_INF;
-    int best_k = 0x7fffffff;
+    int best_k = 0x7fffffff, best_c = 0;
     for (int k = lane; k < cnt; k += 32) {
+      const int c = child ? P.e_child[base + k] : 0;
       double s = edge_score(P.e_visits[base + k], P.e_value[base + k], P.e_prior[base + k], P.e_result[base + k],
                             VL ? (int)P.e_vloss[base + k] : 0);
       if (s > best_s) {
         best_s = s;
         best_k = k;
+        best_c = c;
       }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       double os = __shfl_xor_sync(0xffffffffu, best_s, off);
       int ok = __shfl_xor_sync(0xffffffffu, best_k, off);
+      int oc = __shfl_xor_sync(0xffffffffu, best_c, off);
       if (os > best_s || (os == best_s && ok < best_k)) {
         best_s = os;
         best_k = ok;
+        best_c = oc;
       }
     }
+    if (child) *child = best_c;
     return best_k;
   }
 };
@@ -304,10 +311,11 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
       break;
     }
     if (n.n_exp < n.n_legal) break;
-    const int e = n.edge0 + scan(n);
+    int next;
+    const int e = n.edge0 + scan(n, &next);
     if (lane == (depth & 31)) my_edge = e;
     ++depth;
-    node = P.e_child[(long long)g * P.EA + e];
+    node = next;
   }
   if (term) {
     if (depth <= P.path_cap) P.s_path[(long long)g * 32 + lane] = my_edge;
@@ -482,6 +490,9 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, PolicyView pv,
   const int child = P.s_node[slot];
   const u16* moves1 = P.s_moves + (long long)slot * MAX_MOVES;
   const int n1 = P.s_nmoves[slot];
+  // (issued now, used by reply_child_warp after the gather below: the record's lines are on their way meanwhile)
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.nodes[(long long)g * P.NN + child]));
+  asm volatile("prefetch.global.L2 [%0];" ::"l"((const char*)&P.nodes[(long long)g * P.NN + child] + 128));
   float best_p = -CUDART_INF_F;
   int best_i = 0x7fffffff;
   for (int i = lane; i < n1; i += 32) {
