@@ -74,6 +74,7 @@ SIGNATURES = {
     "crl_games_policy_move_host": (ctypes.c_int, [vp, c_u8p, c_u16p]),
     "crl_mcts_begin_move": (ctypes.c_int, [vp]),
     "crl_set_reuse": (ctypes.c_int, [vp, ctypes.c_int]),
+    "crl_mcts_set_row_bound": (ctypes.c_int, [vp, ctypes.c_int]),
     "crl_reuse_count_host": (ctypes.c_int, [vp, c_i64p]),
     "crl_mcts_simulate": (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int]),
     "crl_mcts_root_stats_host": (ctypes.c_int, [vp, c_i32p, c_f64p, c_f32p, c_u16p, c_u16p, c_i8p, c_i32p, c_i32p, c_f64p]),

@@ -108,8 +108,8 @@ static int check_pool_errors(crl_engine_impl* e) {
     // on this engine fail (the offending lanes keep whatever partial state they have; callers reload them)
     CRL_CUDA(cudaMemsetAsync(e->P.err, 0, sizeof(int), e->stream));
     CRL_CUDA(cudaMemsetAsync(e->P.g_prev_root, 0xFF, sizeof(int) * (size_t)e->G, e->stream));   // no reuse of a broken tree
-    set_error("pool overflow on the device (flags %d: 1 = nodes per game, 2 = edges per game, 4 = plies per game); "
-              "create the engine with larger max_nodes / avg_moves", err);
+    set_error("pool overflow on the device (flags %d: 1 = nodes per game, 2 = edges per game, 4 = plies per game, 8 = more "
+              "running games than crl_mcts_set_row_bound promised); create the engine with larger max_nodes / avg_moves", err);
     return CRL_ENOMEM;
   }
   return CRL_OK;
@@ -250,6 +250,7 @@ int crl_create_ex(crl_engine** out, int device, int max_games, int max_nodes, in
   e->Kmax = max_inflight;
   e->R = max_games * max_inflight;
   e->cur_rows = max_games;
+  e->P.row_cap = max_games * max_inflight;
   e->NN = max_nodes + 1;
   if (avg_moves <= 0) avg_moves = 64;
   long long ea = (long long)e->NN * avg_moves;
@@ -834,6 +835,12 @@ int crl_set_reuse(crl_engine* e, int enable) {
   CRL_CUDA(cudaMemsetAsync(e->P.g_prev_root, 0xFF, sizeof(int) * (size_t)e->G, e->stream));
   e->reuse = enable != 0;
   e->tree_ready = false;
+  return CRL_OK;
+}
+
+int crl_mcts_set_row_bound(crl_engine* e, int max_running_games) {
+  CHECK_ENGINE(e);
+  e->row_bound = max_running_games > 0 && max_running_games < e->G ? max_running_games : 0;
   return CRL_OK;
 }
 

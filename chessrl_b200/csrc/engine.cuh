@@ -33,6 +33,7 @@ struct crl_engine_impl {
   int Kmax = 1;                    // in-flight simulations per game the workspaces are sized for
   int R = 0;                       // evaluation row capacity = G * Kmax
   int cur_rows = 0;                // host bound on the rows of the batch being launched (G, or G*K in wave mode)
+  int row_bound = 0;               // crl_mcts_set_row_bound: at most this many games are running (0 = no promise)
   Pools P{};                       // device pointers
   std::vector<void*> allocs;       // everything cudaMalloc'ed
   int16_t* d_label_of = nullptr;   // [5][64][64]

@@ -27,6 +27,14 @@ namespace crl {
 static constexpr int TREE_BLOCK = 128;
 static constexpr int TREE_WARPS = TREE_BLOCK / 32;
 
+// next row of a compacted evaluation batch.  The launches that follow cover P.row_cap rows (all lanes, or fewer when the
+// host promised an upper bound on the running games): a row beyond that would silently go unevaluated, so it is an error.
+__device__ __forceinline__ int take_row(const Pools& P, int* counter) {
+  const int r = atomicAdd(counter, 1);
+  if (r >= P.row_cap) atomicOr(P.err, ERR_ROW_OVERFLOW);
+  return r;
+}
+
 __device__ __forceinline__ bool game_running(const Pools& P, int g) {
   return P.g_active[g] && P.g_result[g] == RESULT_NONE;
 }
@@ -360,7 +368,7 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
       P.s_node[g] = child;
       P.s_kind[g] = kind;
       if (kind == KIND_EVAL_LEAF) {                // (defensive) the twin's evaluation did not fit: run it
-        const int rb = atomicAdd(n_b, 1);
+        const int rb = take_row(P, n_b);
         list_b[rb] = g;
         P.s_row[g] = rb;
       }
@@ -371,7 +379,7 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_select_expand(Pools P, Policy
   P.s_node[g] = child;
   P.s_kind[g] = kind;
   if (kind == KIND_NEED_REPLY) {
-    int row = atomicAdd(P.eval_n, 1);
+    int row = take_row(P, P.eval_n);
     P.eval_list[row] = g;
     P.s_row[g] = row;
   }
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_select_wave(Pools P) {
       P.s_kind[slot] = kind;
       if (kind != KIND_IDLE) vloss_add(P, g, leaf, 1);
       if (kind == KIND_NEED_REPLY) {
-        const int row = atomicAdd(P.eval_n, 1);
+        const int row = take_row(P, P.eval_n);
         P.eval_list[row] = slot;
         P.s_row[slot] = row;
       }
@@ -516,7 +524,7 @@ __global__ void __launch_bounds__(TREE_BLOCK, 7) k_reply(Pools P, PolicyView pv,
   if (lane != 0) return;
   P.s_kind[slot] = kind;
   if (kind == KIND_EVAL_LEAF) {
-    int rb = atomicAdd(n_b, 1);
+    int rb = take_row(P, n_b);
     list_b[rb] = slot;
     P.s_row[slot] = rb;
   }
@@ -547,7 +555,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_root_init(Pools P, const u8* __r
     atomicAdd((unsigned long long*)&P.counters[2], 1ull);
     return;
   }
-  int row = atomicAdd(P.eval_n, 1);
+  int row = take_row(P, P.eval_n);
   P.eval_list[row] = g;
   P.s_row[g] = row;
 }
@@ -710,6 +718,14 @@ int launch_game_moves(crl_engine_impl* e, const u16* mv, u8* accepted) {
 }
 
 
+// rows the evaluation kernels are launched for: every lane (times K), or the host's promise (crl_mcts_set_row_bound)
+static void set_rows(crl_engine_impl* e, int K) {
+  long long rows = (long long)e->G * K;
+  if (e->row_bound > 0 && (long long)e->row_bound * K < rows) rows = (long long)e->row_bound * K;
+  e->cur_rows = (int)rows;
+  e->P.row_cap = (int)rows;
+}
+
 static int use_list(crl_engine_impl* e, int which) {
   e->P.eval_list = e->d_list[which];
   e->P.eval_n = e->d_n + which;
@@ -730,7 +746,7 @@ int tree_begin_move(crl_engine_impl* e, const u8* mask_dev, bool use_prev) {
   use_list(e, 0);
   e->P.K = 1;                 // root batch: one row per game
   e->P.reuse = e->reuse ? 1 : 0;
-  e->cur_rows = e->G;
+  set_rows(e, 1);
   {
     LaunchScope ls(e, KC_TREE);
     k_root_init<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, mask_dev, use_prev ? 1 : 0);
@@ -752,7 +768,7 @@ static int one_simulation(crl_engine_impl* e) {
   use_list(e, 0);
   e->P.K = 1;
   e->P.reuse = e->reuse ? 1 : 0;
-  e->cur_rows = e->G;
+  set_rows(e, 1);
   {
     LaunchScope ls(e, KC_TREE);
     k_select_expand<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(
@@ -786,7 +802,7 @@ static int one_wave(crl_engine_impl* e, int K) {
   use_list(e, 0);
   e->P.K = K;
   e->P.reuse = 0;             // the wave schedule evaluates everything (twins are looked up in the exact schedule only)
-  e->cur_rows = e->G * K;
+  set_rows(e, K);
   {
     LaunchScope ls(e, KC_TREE);
     k_select_wave<<<div_up((long long)e->G * 32, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P);
@@ -869,7 +885,8 @@ int tree_run_steps(crl_engine_impl* e, int n_sims, int K) {
   const int par = e->tree_parity & 1;
   const unsigned long long key = 1ull + (unsigned long long)e->eval_kind + 2ull * (unsigned long long)e->eval_bits +
                                  64ull * (e->eval_seed * 0x9E3779B97F4A7C15ull) + 0x100000000ull * (unsigned long long)K +
-                                 (e->reuse ? 0x8000000000000000ull : 0ull);
+                                 (e->reuse ? 0x8000000000000000ull : 0ull) +
+                                 0x9E3779B97F4A7C15ull * (unsigned long long)(e->row_bound > 0 ? e->row_bound : 0);
   if (e->sim_graph[par] == nullptr || e->sim_graph_key[par] != key) {
     if (e->sim_graph[par]) {
       cudaGraphExecDestroy(e->sim_graph[par]);
@@ -908,7 +925,10 @@ int tree_run_steps(crl_engine_impl* e, int n_sims, int K) {
 
 int tree_policy_move(crl_engine_impl* e, const u8* mask_dev, u16* picks_dev) {
   CRL_CUDA(cudaMemsetAsync(picks_dev, 0xFF, sizeof(u16) * e->G, e->stream));
+  const int bound = e->row_bound;
+  e->row_bound = 0;                               // the bound is a promise about the NEXT search, not about this call
   int rc = tree_begin_move(e, mask_dev, false);   // root_init + evaluation of the current positions
+  e->row_bound = bound;
   if (rc != CRL_OK) return rc;
   LaunchScope ls(e, KC_TREE);
   k_policy_move<<<div_up(e->G, TREE_BLOCK), TREE_BLOCK, 0, e->stream>>>(e->P, e->pview, e->d_label_of, picks_dev);

@@ -27,7 +27,7 @@ namespace crl {
 enum { HIST_RING = 8, KEY_RING = 128, MAX_GAME_PLIES = 2048 };
 enum { KIND_IDLE = 0, KIND_TERMINAL = 1, KIND_NEED_REPLY = 2, KIND_NEW_TERMINAL = 3, KIND_EVAL_LEAF = 4,
        KIND_EVAL_REUSED = 5 };   // new leaf whose value / priors came from its twin in the previous move's tree
-enum { ERR_NODE_OVERFLOW = 1, ERR_EDGE_OVERFLOW = 2, ERR_PLY_OVERFLOW = 4 };
+enum { ERR_NODE_OVERFLOW = 1, ERR_EDGE_OVERFLOW = 2, ERR_PLY_OVERFLOW = 4, ERR_ROW_OVERFLOW = 8 };
 
 struct NodeRec {
   u64 p2[9];      // state of the node (after the reply; = p1 when the game ended on our move)
@@ -92,6 +92,7 @@ struct Pools {
   int* g_sims_left; // [G] simulations of the current crl_mcts_simulate call still to run (wave mode)
   int* eval_list;   // [G*K] slot of every batch row
   int* eval_n;      // [1]
+  int row_cap;      // rows the evaluation kernels of this launch sequence cover (G*K, or the host's bound: crl_mcts_set_row_bound)
   int* err;         // [1] ERR_* flags
   long long* counters;  // [0] simulations [1] evaluations run [2] evaluations taken from the previous tree instead
 };

@@ -323,6 +323,11 @@ class Engine:
         check(self.lib.crl_set_reuse(self.h, int(bool(enable))))
         self.reuse = bool(enable)
 
+    def set_row_bound(self, max_running_games=0):
+        """Promise that at most this many games are running (0 = none): launches shrink to that many rows and small batches
+        take the tower's single-tile path (include/chessrl_b200.h crl_mcts_set_row_bound).  A broken promise raises."""
+        check(self.lib.crl_mcts_set_row_bound(self.h, int(max_running_games)))
+
     def mcts_simulate(self, n_sims, inflight=1):
         check(self.lib.crl_mcts_simulate(self.h, int(n_sims), int(inflight)))
 

@@ -15,6 +15,9 @@ from . import boards as B
 from ._lib import EVAL_NET
 
 
+SMALL_BATCH_ROWS = 296      # 74 CTA pairs x 4 boards: the largest batch the tower runs one tile per pair
+
+
 def compute_policy(child_visits, root_visits, n_plies, noise=True):
     """SelfPlayTree.compute_policy (mctree.py:305-322) from the root statistics of one game."""
     if n_plies < 30:
@@ -155,6 +158,12 @@ class LockstepSelfPlay:
     def step(self):
         """One agent move (+ reply) for every running game.  Returns the (our move, reply) words [n, 2]."""
         e = self.e
+        # the drain of a finite run: once few lanes still hold a game, tell the engine, so that its launches cover those
+        # rows only and the evaluations take the tower's single-tile path (two regimes only: the simulation graph is
+        # re-captured when the bound changes)
+        n_run = int(self.running().sum())
+        small = SMALL_BATCH_ROWS // max(1, self.inflight)
+        e.set_row_bound(small if 0 < n_run <= small < e.max_games else 0)
         e.mcts_begin_move()
         e.mcts_simulate(self.sims, self.inflight)
         st = e.root_stats(want=("visits",))

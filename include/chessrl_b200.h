@@ -210,6 +210,13 @@ int crl_mcts_begin_move(crl_engine* e);
  * (set / restart / play / policy move) unlinks it.  Exact schedule (inflight = 1) only; waves evaluate everything.
  * crl_reuse_count_host: evaluations taken from the previous tree so far (crl_counters_host counts only those run). */
 int crl_set_reuse(crl_engine* e, int enable);
+/* A promise by the host that at most max_running_games games are running (active and unfinished) until it says otherwise
+ * (0 = no promise).  The evaluation batches are compacted on the device, so the engine otherwise sizes every launch for all
+ * max_games lanes; with a bound the launches shrink, and a batch bound of at most 296 positions runs the tower's single-tile
+ * instantiation (one 4-board tile per CTA pair: ~1.2 x faster evaluations) -- the drain of a finite selfplay.py run
+ * (selfplay.py:142-163), when few of the lanes still hold a game.  A broken promise is detected on the device and
+ * reported as CRL_ENOMEM by the next call that checks the pools; nothing is evaluated silently wrong. */
+int crl_mcts_set_row_bound(crl_engine* e, int max_running_games);
 int crl_reuse_count_host(crl_engine* e, int64_t* reused_host);
 /* n_sims x SelfPlayTree.explore_tree (mctree.py:200-214) for every running game in lockstep.
  * inflight = 1: the deterministic threads=1 schedule.

@@ -35,6 +35,9 @@ class FakeEngine:
     def set_reuse(self, enable=True):
         pass
 
+    def set_row_bound(self, max_running_games=0):
+        pass
+
     def close(self):
         pass
 

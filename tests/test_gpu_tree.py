@@ -304,3 +304,45 @@ def test_wave_call_followed_by_exact_call_on_the_same_tree():
     c = e.counters()
     assert c["simulations"] == 16 * total
     e.close()
+
+
+def test_row_bound_shrinks_the_launches_and_a_broken_promise_is_reported():
+    """crl_mcts_set_row_bound: with 100 of 400 lanes running, a bound of 296 rows makes every launch cover 296 rows (and the
+    tower take its single-tile path) -- same trees as without the bound, hash evaluator and real network; promising 50
+    while 100 games run is reported, not evaluated silently wrong; the engine works again after the report."""
+    import netpacks
+    from chessrl_b200._lib import EVAL_NET, CrlError
+    from chessrl_b200.engine import Engine
+    e = Engine(max_games=400, max_nodes=41, avg_moves=96)
+    recs = np.tile(B.record_from_fen(), (400, 1))
+    mls = [[B.uci_to_move(m) for m in (["e2e4", "e7e5", "g1f3", "b8c6"][:g % 5])] for g in range(400)]
+    active = np.zeros(400, dtype=np.uint8)
+    active[::4] = 1                                            # 100 running games, scattered over the lanes
+
+    def search(bound):
+        e.games_set(recs, mls)
+        e.games_set_active(active)
+        e.set_row_bound(bound)
+        e.mcts_begin_move()
+        e.mcts_simulate(40)
+        return e.root_stats()
+
+    try:
+        for kind in ("hash", "net"):
+            if kind == "hash":
+                e.set_evaluator(EVAL_HASH, 11, 24)
+            else:
+                e.load_weights(netpacks.lively_pack())
+                e.set_evaluator(EVAL_NET)
+            free, bounded = search(0), search(296)
+            for k in free:
+                assert np.array_equal(free[k], bounded[k]), (kind, k)
+            assert (bounded["n_children"][::4] > 0).all() and (bounded["n_children"][1::4] == 0).all()
+        with pytest.raises(CrlError):
+            search(50)
+        again = search(0)                                      # the error was reported once; the engine is usable again
+        for k in again:
+            assert np.array_equal(again[k], free[k]), k
+    finally:
+        e.set_row_bound(0)
+        e.close()
