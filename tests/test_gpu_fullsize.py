@@ -122,3 +122,51 @@ def test_encode_full_batch_properties():
     turn = (boards[8] & 1).float()
     assert bool((p[..., 126] == turn[:, None, None]).all())
     e.close()
+
+
+def test_full_size_evaluation_reuse_is_invisible():
+    """BASELINE configs[3] scale: 4,096 lanes, real network, three lockstep moves with the most-visited child played --
+    evaluation reuse on and off give identical root statistics for every lane, and with reuse on the second and third
+    searches run a fraction of the evaluations."""
+    import netpacks
+    from chessrl_b200._lib import EVAL_NET
+    from chessrl_b200.engine import Engine
+    from chessrl_b200.lockstep import LockstepSelfPlay
+    G, sims = 4096, 48
+    e = Engine(max_games=G, max_nodes=sims + 1, avg_moves=120)
+    e.load_weights(netpacks.lively_pack())
+    e.set_evaluator(EVAL_NET)
+    rng = random.Random(5)
+    openings = [["e2e4", "e7e5"], ["d2d4", "d7d5"], ["g1f3", "g8f6"], ["c2c4", "e7e6", "b1c3", "d7d5"], []]
+    mls = [[B.uci_to_move(m) for m in rng.choice(openings)] for _ in range(G)]
+    recs = np.tile(B.record_from_fen(), (G, 1))
+
+    def run(reuse):
+        sp = LockstepSelfPlay(e, n_games=G, sims=sims, noise=False, reuse=reuse)
+        sp.start(start_records=recs, move_lists=mls)
+        out, evals = [], []
+        for _ in range(3):
+            c0 = e.counters()
+            e.mcts_begin_move()
+            e.mcts_simulate(sims, 1)
+            st = e.root_stats(want=("visits", "values", "priors"))
+            out.append(st)
+            picks = np.where(st["n_children"] > 0, np.argmax(st["visits"], axis=1), -1).astype(np.int32)
+            e.commit(picks, apply=True)
+            sp._read_status()
+            c1 = e.counters()
+            evals.append((c1["evaluations"] - c0["evaluations"], c1["reused_evaluations"] - c0["reused_evaluations"]))
+        return out, evals
+
+    try:
+        off, ev_off = run(False)
+        on, ev_on = run(True)
+        for a, b in zip(off, on):
+            for k in a:
+                assert np.array_equal(a[k], b[k]), k
+        assert ev_on[0] == ev_off[0] and ev_on[0][1] == 0
+        for (run_on, reused), (run_off, _) in zip(ev_on[1:], ev_off[1:]):
+            assert run_on + reused == run_off and run_on < 0.7 * run_off, (ev_on, ev_off)
+    finally:
+        e.set_reuse(False)
+        e.close()
