@@ -664,7 +664,8 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __res
   u16 m0 = MOVE_NONE, m1 = MOVE_NONE;
   const int k = pick[g];
   const NodeRec& root = P.nodes[(long long)g * P.NN];
-  if (P.g_active[g] && k >= 0 && k < root.n_exp) {
+  const bool has_tree = P.g_active[g] && P.g_nnodes[g] > 0;      // (a lane without a running game got no tree this move)
+  if (has_tree && k >= 0 && k < root.n_exp) {
     const NodeRec& c = P.nodes[(long long)g * P.NN + P.e_child[(long long)g * P.EA + root.edge0 + k]];
     if (c.reply != MOVE_NONE) {
       m0 = c.move;             // move_stack[-2] = our move, [-1] = the opponent's reply
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(TREE_BLOCK) k_commit(Pools P, const int* __res
   out_moves[2 * g] = m0;
   out_moves[2 * g + 1] = m1;
   int next_root = -1;
-  if (apply && P.g_active[g] && k >= 0) {
+  if (apply && has_tree && k >= 0) {
     const int ok0 = game_move(P, g, m0);       // selfplay.py:77-78: Game.move silently rejects an illegal first move
     const int ok1 = game_move(P, g, m1);
     // the game now stands where the chosen child stands: the next search may take evaluations from this tree
