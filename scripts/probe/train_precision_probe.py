@@ -51,6 +51,9 @@ def grads_fp64():
 
 
 ref = grads_fp64()
+if len(sys.argv) > 1 and sys.argv[1] == "benchmark":
+    torch.backends.cudnn.benchmark = True
+    print("torch.backends.cudnn.benchmark = True (cuDNN picks the fastest algorithm per convolution shape by timing)")
 for mode in ("fp32", "tf32x3", "tf32", "bf16"):
     t, lp, lv, gr = grads_of(mode)
     gr = [x.double() for x in gr]
